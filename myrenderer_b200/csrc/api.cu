@@ -1,0 +1,592 @@
+// api.cu -- the extern "C" surface of libmyrenderer_b200: context, memory helpers, argument
+// validation, host<->device staging, and the host-side helpers (layout presets, partitions,
+// unirand host restatement).  Kernels live in terrain.cu / triangulate.cu / synth.cu.
+#include <algorithm>
+#include <new>
+#include "common.cuh"
+#include "unirand.cuh"
+
+int mr_heightmap_normalize_impl(mr_context* ctx, const uint16_t* in, uint64_t count, float* out);
+int mr_polygon_offsets_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t* first_tri_dev);
+int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t seed,
+                               uint64_t poly_index0, uint32_t* out_dev);
+int mr_synth_heightmap_u16_impl(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t row0, uint32_t rows,
+                                uint16_t* out_dev);
+int mr_synth_polygons_impl(mr_context* ctx, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point_dev,
+                           uint32_t npoly, float* xy_dev);
+
+namespace {
+// unirand.zig:24 (host copy for mr_unirand_seed_host)
+const uint32_t k_primes_host[MR_NPRIMES] = {
+    2,    3,    5,    7,    11,   13,   17,   19,   23,   29,   31,   37,   41,   43,
+    47,   53,   59,   61,   67,   71,   73,   79,   83,   89,   97,   101,  103,  107,
+    109,  113,  127,  131,  137,  139,  149,  151,  157,  163,  167,  173,  179,  181,
+    191,  193,  197,  199,  211,  223,  227,  229,  233,  239,  241,  251,  257,  263,
+    269,  271,  277,  281,  283,  293,  307,  311,  313,  317,  331,  337,  347,  349,
+    353,  359,  367,  373,  379,  383,  389,  397,  401,  409,  419,  421,  431,  433,
+    439,  443,  449,  457,  461,  463,  467,  479,  487,  491,  499,  503,  509,  521,
+    523,  541,  601,  659,  733,  809,  863,  941,  1013, 1069, 1151, 1283, 1289, 1367,
+    1447, 1499, 1579, 1637, 1723, 429494501u, 429493501u, 429486647u, 100001053u, 100002421u,
+    10001567u};
+
+bool layout_ok(const mr_layout* L, uint32_t need_attrs, uint32_t ncomp0) {
+    if (!L || L->nattr < need_attrs || L->nattr > MR_MAX_ATTR) return false;
+    if (L->stride < 8 || L->stride > 256 || (L->stride & 3u)) return false;
+    for (uint32_t i = 0; i < L->nattr; ++i) {
+        if (L->attr[i].offset & 3u) return false;
+        if (L->attr[i].ncomp < 2 || L->attr[i].ncomp > 4) return false;
+        if (L->attr[i].offset + 4u * L->attr[i].ncomp > L->stride) return false;
+    }
+    if (L->attr[0].ncomp < ncomp0) return false;
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+int mr_abi_version(void) { return MR_ABI_VERSION; }
+
+int mr_device_count(int* count_out) {
+    if (!count_out) return MR_E_BADARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count_out = 0;
+        return MR_E_CUDA;
+    }
+    *count_out = n;
+    return MR_OK;
+}
+
+int mr_context_create(int device, mr_context** ctx_out) {
+    if (!ctx_out) return MR_E_BADARG;
+    *ctx_out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return MR_E_CUDA;  // no CPU fallback
+    }
+    if (device < 0 || device >= n) return MR_E_BADARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MR_E_CUDA;
+    mr_context* ctx = new (std::nothrow) mr_context();
+    if (!ctx) return MR_E_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return MR_E_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return MR_E_CUDA;
+    }
+    ctx->own_stream = true;
+    *ctx_out = ctx;
+    return MR_OK;
+}
+
+int mr_context_destroy(mr_context* ctx) {
+    if (!ctx) return MR_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < MR_NUM_SCRATCH; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->pinned_mailbox) cudaFreeHost(ctx->pinned_mailbox);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MR_OK;
+}
+
+int mr_context_set_stream(mr_context* ctx, void* cuda_stream) {
+    if (!ctx) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return MR_OK;
+}
+
+int mr_context_stream(mr_context* ctx, void** cuda_stream_out) {
+    if (!ctx || !cuda_stream_out) return MR_E_BADARG;
+    *cuda_stream_out = ctx->stream;
+    return MR_OK;
+}
+
+int mr_sync(mr_context* ctx) {
+    if (!ctx) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+const char* mr_last_error(const mr_context* ctx) { return ctx ? ctx->err : "null context"; }
+uint64_t mr_launch_count(const mr_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int mr_device_alloc(mr_context* ctx, size_t bytes, void** dev_out) {
+    if (!ctx || !dev_out) return MR_E_BADARG;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(dev_out, bytes ? bytes : 16);
+    if (e != cudaSuccess) return mr_fail(ctx, MR_E_NOMEM, "cudaMalloc", e);
+    return MR_OK;
+}
+int mr_device_free(mr_context* ctx, void* dev) {
+    if (!ctx) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MR_CUDA(ctx, cudaFree(dev));
+    return MR_OK;
+}
+int mr_pinned_alloc(mr_context* ctx, size_t bytes, void** host_out) {
+    if (!ctx || !host_out) return MR_E_BADARG;
+    cudaError_t e = cudaMallocHost(host_out, bytes ? bytes : 16);
+    if (e != cudaSuccess) return mr_fail(ctx, MR_E_NOMEM, "cudaMallocHost", e);
+    return MR_OK;
+}
+int mr_pinned_free(mr_context* ctx, void* host) {
+    if (!ctx) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaFreeHost(host));
+    return MR_OK;
+}
+int mr_copy(mr_context* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || (!dst && bytes) || (!src && bytes)) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return MR_OK;
+}
+int mr_fill_zero(mr_context* ctx, void* dev, size_t bytes) {
+    if (!ctx || (!dev && bytes)) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaMemsetAsync(dev, 0, bytes, ctx->stream));
+    return MR_OK;
+}
+
+int mr_layout_preset(int which, mr_layout* out) {
+    if (!out) return MR_E_BADARG;
+    memset(out, 0, sizeof(*out));
+    out->stride = 32;
+    out->nattr = 2;
+    out->attr[0].location = 0;
+    out->attr[1].location = 1;
+    switch (which) {
+        case MR_LAYOUT_GPUVERTEX_DECL:
+            out->attr[0] = {0, 2, 0};
+            out->attr[1] = {16, 3, 1};
+            return MR_OK;
+        case MR_LAYOUT_GPUVERTEX_ZIGAUTO:
+            out->attr[0] = {16, 2, 0};
+            out->attr[1] = {0, 3, 1};
+            return MR_OK;
+        case MR_LAYOUT_TERRAINVERTEX:
+            out->attr[0] = {0, 3, 0};
+            out->attr[1] = {16, 3, 1};
+            return MR_OK;
+        default: return MR_E_BADARG;
+    }
+}
+
+int mr_terrain_params_default(mr_terrain_params* out) {
+    if (!out) return MR_E_BADARG;
+    out->grid_step = 0.2f;     // Terrain.zig:36
+    out->origin_scale = 0.1f;  // Terrain.zig:36
+    out->height_scale = 5.0f;  // Terrain.zig:48
+    return MR_OK;
+}
+
+int mr_terrain_describe(uint32_t n, const mr_terrain_params* params, float bbox_min[3], float bbox_max[3],
+                        uint64_t* vertex_count, uint64_t* index_count) {
+    mr_terrain_params p;
+    if (params) p = *params; else mr_terrain_params_default(&p);
+    if (n == 0) return MR_E_BADARG;
+    const float bound = (float)n * p.origin_scale;  // Terrain.zig:103-104
+    if (bbox_min) {
+        bbox_min[0] = -bound;
+        bbox_min[1] = 0.0f;
+        bbox_min[2] = -bound;
+    }
+    if (bbox_max) {  // Terrain.zig:109: (bound, 5.0, bound); 5.0 is height_scale * 1.0
+        bbox_max[0] = bound;
+        bbox_max[1] = p.height_scale;
+        bbox_max[2] = bound;
+    }
+    if (vertex_count) *vertex_count = (uint64_t)n * n;
+    if (index_count) *index_count = 6ull * (uint64_t)(n - 1) * (uint64_t)(n - 1);
+    return MR_OK;
+}
+
+int mr_terrain_build(mr_context* ctx, const mr_terrain_job* job) {
+    if (!ctx || !job) return MR_E_BADARG;
+    const mr_terrain_job& j = *job;
+    if (j.n == 0 || j.n > 65535u || !j.height) return mr_fail(ctx, MR_E_BADARG, "terrain: n must be 1..65535 and height non-null");
+    if (j.height_fmt != MR_HEIGHT_U16 && j.height_fmt != MR_HEIGHT_F32) return mr_fail(ctx, MR_E_BADARG, "terrain: bad height_fmt");
+    if (j.row_begin > j.row_end || j.row_end > j.n) return mr_fail(ctx, MR_E_BADARG, "terrain: bad row range");
+    if (j.qrow_begin > j.qrow_end || j.qrow_end > j.n - 1u) return mr_fail(ctx, MR_E_BADARG, "terrain: bad quad-row range");
+    if (j.vtx_out && !layout_ok(&j.layout, 1, 3)) return mr_fail(ctx, MR_E_BADARG, "terrain: bad vertex layout");
+    if (j.vtx_out && j.layout.nattr > 1 && j.layout.attr[1].ncomp < 3) return mr_fail(ctx, MR_E_BADARG, "terrain: normal needs 3 components");
+    if (j.vtx_out && j.row_end > j.row_begin) {
+        const uint32_t need_lo = j.row_begin > 0 ? j.row_begin - 1 : 0;
+        const uint32_t need_hi = std::min(j.row_end + 1, j.n);
+        if (j.height_row0 > need_lo || (uint64_t)j.height_row0 + j.height_rows < need_hi)
+            return mr_fail(ctx, MR_E_BADARG, "terrain: height rows do not cover the band plus halo");
+        if (j.vtx_row0 > j.row_begin) return mr_fail(ctx, MR_E_BADARG, "terrain: vtx_row0 > row_begin");
+    }
+    if (j.idx_out && j.qrow_end > j.qrow_begin && j.idx_qrow0 > j.qrow_begin) return mr_fail(ctx, MR_E_BADARG, "terrain: idx_qrow0 > qrow_begin");
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    mr_terrain_job d = j;
+    const size_t texel = j.height_fmt == MR_HEIGHT_U16 ? 2 : 4;
+    const void* hdev = nullptr;
+    int rc = mr_stage_in(ctx, 0, j.height, (size_t)j.height_rows * j.n * texel, &hdev);
+    if (rc) return rc;
+    d.height = hdev;
+    bool vs = false, is = false;
+    void* vdev = nullptr;
+    void* idev = nullptr;
+    const size_t vbytes = (size_t)(j.row_end - j.vtx_row0) * j.n * j.layout.stride;
+    const size_t ibytes = j.n > 1 ? (size_t)(j.qrow_end - j.idx_qrow0) * 6u * (j.n - 1u) * 4u : 0;
+    if (j.vtx_out) {
+        rc = mr_stage_out(ctx, 4, j.vtx_out, vbytes, &vdev, &vs);
+        if (rc) return rc;
+        d.vtx_out = vdev;
+    }
+    if (j.idx_out) {
+        rc = mr_stage_out(ctx, 5, j.idx_out, ibytes, &idev, &is);
+        if (rc) return rc;
+        d.idx_out = static_cast<uint32_t*>(idev);
+    }
+    rc = mr_terrain_build_impl(ctx, &d);
+    if (rc) return rc;
+    if (vs) {
+        // only rows [row_begin,row_end) were produced
+        const size_t off = (size_t)(j.row_begin - j.vtx_row0) * j.n * j.layout.stride;
+        rc = mr_copy_back(ctx, static_cast<unsigned char*>(j.vtx_out) + off, static_cast<unsigned char*>(vdev) + off,
+                          (size_t)(j.row_end - j.row_begin) * j.n * j.layout.stride);
+        if (rc) return rc;
+    }
+    if (is) {
+        const size_t L = 6u * (size_t)(j.n - 1u) * 4u;
+        const size_t off = (size_t)(j.qrow_begin - j.idx_qrow0) * L;
+        rc = mr_copy_back(ctx, reinterpret_cast<unsigned char*>(j.idx_out) + off, static_cast<unsigned char*>(idev) + off,
+                          (size_t)(j.qrow_end - j.qrow_begin) * L);
+        if (rc) return rc;
+    }
+    if (vs || is) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+int mr_terrain_build_full(mr_context* ctx, const void* height, uint32_t height_fmt, uint32_t n, const mr_layout* layout,
+                          const mr_terrain_params* params, void* vtx_out, uint32_t* idx_out) {
+    if (!ctx) return MR_E_BADARG;
+    mr_terrain_job j;
+    memset(&j, 0, sizeof(j));
+    j.n = n;
+    j.height_fmt = height_fmt;
+    j.height = height;
+    j.height_row0 = 0;
+    j.height_rows = n;
+    j.row_begin = 0;
+    j.row_end = n;
+    j.vtx_out = vtx_out;
+    j.vtx_row0 = 0;
+    j.qrow_begin = 0;
+    j.qrow_end = n ? n - 1 : 0;
+    j.idx_out = idx_out;
+    j.idx_qrow0 = 0;
+    if (layout) j.layout = *layout; else mr_layout_preset(MR_LAYOUT_TERRAINVERTEX, &j.layout);
+    if (params) j.params = *params; else mr_terrain_params_default(&j.params);
+    return mr_terrain_build(ctx, &j);
+}
+
+int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, float* out) {
+    if (!ctx || (count && (!in || !out))) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* din = nullptr;
+    int rc = mr_stage_in(ctx, 0, in, (size_t)count * 2, &din);
+    if (rc) return rc;
+    void* dout = nullptr;
+    bool st = false;
+    rc = mr_stage_out(ctx, 4, out, (size_t)count * 4, &dout, &st);
+    if (rc) return rc;
+    rc = mr_heightmap_normalize_impl(ctx, static_cast<const uint16_t*>(din), count, static_cast<float*>(dout));
+    if (rc) return rc;
+    if (st) {
+        rc = mr_copy_back(ctx, out, dout, (size_t)count * 4);
+        if (rc) return rc;
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_polygon_offsets(mr_context* ctx, const uint64_t* first_point, uint32_t npoly, uint64_t* first_tri_out) {
+    if (!ctx || !first_point || !first_tri_out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* dfp = nullptr;
+    int rc = mr_stage_in(ctx, 1, first_point, (size_t)(npoly + 1) * 8, &dfp);
+    if (rc) return rc;
+    void* dft = nullptr;
+    bool st = false;
+    rc = mr_stage_out(ctx, 2, first_tri_out, (size_t)(npoly + 1) * 8, &dft, &st);
+    if (rc) return rc;
+    rc = mr_polygon_offsets_impl(ctx, static_cast<const uint64_t*>(dfp), npoly, static_cast<uint64_t*>(dft));
+    if (rc) return rc;
+    if (st) {
+        rc = mr_copy_back(ctx, first_tri_out, dft, (size_t)(npoly + 1) * 8);
+        if (rc) return rc;
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_polygon_draw_range(uint64_t first_tri_i, uint64_t first_tri_next, uint64_t tri_base, mr_draw_range* out) {
+    if (!out || first_tri_next < first_tri_i || first_tri_i < tri_base) return MR_E_BADARG;
+    const uint64_t prims = first_tri_next - first_tri_i, off = first_tri_i - tri_base;
+    if (prims * 3 > 0xFFFFFFFFull || off * 3 > 0xFFFFFFFFull) return MR_E_BADARG;  // VertexBuffer fields are u32
+    out->vertex_count = (uint32_t)(prims * 3);  // VertexBuffer.zig:21
+    out->instance_count = 1;
+    out->first_vertex = (uint32_t)(off * 3);  // VertexBuffer.zig:22
+    out->first_instance = 0;
+    return MR_OK;
+}
+
+int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job) {
+    if (!ctx || !job) return MR_E_BADARG;
+    const mr_polygon_job& j = *job;
+    if (j.npoly == 0) return MR_OK;
+    if (!j.xy || !j.first_point || !j.first_tri || !j.vtx_out) return mr_fail(ctx, MR_E_BADARG, "polygons: null pointer");
+    if (!layout_ok(&j.layout, 1, 2)) return mr_fail(ctx, MR_E_BADARG, "polygons: bad vertex layout");
+    if (j.layout.nattr > 1 && j.layout.attr[1].ncomp < 3) return mr_fail(ctx, MR_E_BADARG, "polygons: colour needs 3 components");
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    mr_polygon_job d = j;
+    const bool fp_dev = mr_is_device_ptr(j.first_point);
+    const bool ft_dev = mr_is_device_ptr(j.first_tri);
+    // sizes of the data arrays: known from first_point/first_tri when those live on the host
+    uint64_t npts = 0, ntri = 0;
+    bool need_sizes = !mr_is_device_ptr(j.xy) || !mr_is_device_ptr(j.vtx_out);
+    if (need_sizes) {
+        uint64_t fp_ends[2], ft_ends[2];
+        if (fp_dev) {
+            MR_CUDA(ctx, cudaMemcpyAsync(&fp_ends[0], j.first_point, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MR_CUDA(ctx, cudaMemcpyAsync(&fp_ends[1], j.first_point + j.npoly, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            fp_ends[0] = j.first_point[0];
+            fp_ends[1] = j.first_point[j.npoly];
+        }
+        if (ft_dev) {
+            MR_CUDA(ctx, cudaMemcpyAsync(&ft_ends[0], j.first_tri, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MR_CUDA(ctx, cudaMemcpyAsync(&ft_ends[1], j.first_tri + j.npoly, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            ft_ends[0] = j.first_tri[0];
+            ft_ends[1] = j.first_tri[j.npoly];
+        }
+        if (fp_dev || ft_dev) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (fp_ends[0] < j.point_base || ft_ends[0] < j.tri_base) return mr_fail(ctx, MR_E_BADARG, "polygons: base beyond first offset");
+        npts = fp_ends[1] - j.point_base;   // xy covers [point_base, first_point[npoly])
+        ntri = ft_ends[1] - j.tri_base;
+    }
+    const void* p = nullptr;
+    int rc;
+    rc = mr_stage_in(ctx, 0, j.xy, (size_t)npts * 8, &p);
+    if (rc) return rc;
+    d.xy = static_cast<const float*>(p);
+    rc = mr_stage_in(ctx, 1, j.first_point, (size_t)(j.npoly + 1) * 8, &p);
+    if (rc) return rc;
+    d.first_point = static_cast<const uint64_t*>(p);
+    rc = mr_stage_in(ctx, 2, j.first_tri, (size_t)(j.npoly + 1) * 8, &p);
+    if (rc) return rc;
+    d.first_tri = static_cast<const uint64_t*>(p);
+    if (j.offset_prime) {
+        rc = mr_stage_in(ctx, 3, j.offset_prime, (size_t)j.npoly * 8, &p);
+        if (rc) return rc;
+        d.offset_prime = static_cast<const uint32_t*>(p);
+    }
+    bool sv = false, sb = false, ss = false, sn = false;
+    void* q = nullptr;
+    const size_t vbytes = (size_t)ntri * 3u * j.layout.stride;
+    rc = mr_stage_out(ctx, 4, j.vtx_out, vbytes, &q, &sv);
+    if (rc) return rc;
+    d.vtx_out = q;
+    if (j.bbox_out) {
+        rc = mr_stage_out(ctx, 5, j.bbox_out, (size_t)j.npoly * 16, &q, &sb);
+        if (rc) return rc;
+        d.bbox_out = static_cast<float*>(q);
+    }
+    if (j.status_out) {
+        rc = mr_stage_out(ctx, 6, j.status_out, (size_t)j.npoly * 4, &q, &ss);
+        if (rc) return rc;
+        d.status_out = static_cast<uint32_t*>(q);
+    }
+    if (j.ntri_out) {
+        rc = mr_stage_out(ctx, 7, j.ntri_out, (size_t)j.npoly * 4, &q, &sn);
+        if (rc) return rc;
+        d.ntri_out = static_cast<uint32_t*>(q);
+    }
+    rc = mr_triangulate_impl(ctx, &d);
+    if (rc) return rc;
+    if (sv) {
+        // the polygons of this job own [first_tri[0], first_tri[npoly]) only
+        uint64_t ft0 = ft_dev ? 0 : j.first_tri[0];
+        if (ft_dev) {
+            MR_CUDA(ctx, cudaMemcpyAsync(&ft0, j.first_tri, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        const size_t off = (size_t)(ft0 - j.tri_base) * 3u * j.layout.stride;
+        rc = mr_copy_back(ctx, static_cast<unsigned char*>(j.vtx_out) + off, static_cast<unsigned char*>(d.vtx_out) + off, vbytes - off);
+        if (rc) return rc;
+    }
+    if (sb) { rc = mr_copy_back(ctx, j.bbox_out, d.bbox_out, (size_t)j.npoly * 16); if (rc) return rc; }
+    if (ss) { rc = mr_copy_back(ctx, j.status_out, d.status_out, (size_t)j.npoly * 4); if (rc) return rc; }
+    if (sn) { rc = mr_copy_back(ctx, j.ntri_out, d.ntri_out, (size_t)j.npoly * 4); if (rc) return rc; }
+    if (sv || sb || ss || sn) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
+}
+
+uint64_t mr_rng_state0(uint64_t seed, uint64_t index) { return mr_rng_state0_hd(seed, index); }
+
+uint32_t mr_rng_u32(uint64_t* state) {
+    // sequential form of the same stream: draw k of state0 == k-th call starting from state0
+    const uint32_t v = mr_rng_draw(*state, 0u);
+    *state += MR_GOLDEN;
+    return v;
+}
+
+// unirand.zig:26-50, host restatement (same draws as the device port)
+int mr_unirand_seed_host(uint32_t top, uint64_t seed, uint64_t index, uint32_t* offset_out, uint32_t* prime_out) {
+    if (!offset_out || !prime_out) return MR_E_BADARG;
+    if (top == 1u) {
+        *offset_out = 0;
+        *prime_out = 1;
+        return MR_OK;
+    }
+    uint64_t st = mr_rng_state0_hd(seed, index);
+    *offset_out = mr_rng_u32(&st) % (uint32_t)(top - 1u) + 1u;
+    uint32_t best = 1;
+    for (int i = 0; i < MR_NPRIMES; ++i) {
+        const uint32_t p = k_primes_host[i];
+        if (p < top && top % p != 0u) {
+            if (mr_rng_u32(&st) % 3u > 0u) best = p;
+        }
+    }
+    *prime_out = best;
+    return MR_OK;
+}
+
+int mr_unirand_seed_batch(mr_context* ctx, const uint64_t* first_point, uint32_t npoly, uint64_t seed,
+                          uint64_t poly_index0, uint32_t* offset_prime_out) {
+    if (!ctx || !first_point || !offset_prime_out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* dfp = nullptr;
+    int rc = mr_stage_in(ctx, 1, first_point, (size_t)(npoly + 1) * 8, &dfp);
+    if (rc) return rc;
+    void* dout = nullptr;
+    bool st = false;
+    rc = mr_stage_out(ctx, 3, offset_prime_out, (size_t)npoly * 8, &dout, &st);
+    if (rc) return rc;
+    rc = mr_unirand_seed_batch_impl(ctx, static_cast<const uint64_t*>(dfp), npoly, seed, poly_index0,
+                                    static_cast<uint32_t*>(dout));
+    if (rc) return rc;
+    if (st) {
+        rc = mr_copy_back(ctx, offset_prime_out, dout, (size_t)npoly * 8);
+        if (rc) return rc;
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_synth_heightmap_u16(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t row0, uint32_t rows, uint16_t* out) {
+    if (!ctx || !out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* dout = nullptr;
+    bool st = false;
+    const size_t bytes = (size_t)rows * n * 2;
+    int rc = mr_stage_out(ctx, 4, out, bytes, &dout, &st);
+    if (rc) return rc;
+    rc = mr_synth_heightmap_u16_impl(ctx, seed, n, row0, rows, static_cast<uint16_t*>(dout));
+    if (rc) return rc;
+    if (st) {
+        rc = mr_copy_back(ctx, out, dout, bytes);
+        if (rc) return rc;
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_synth_polygons(mr_context* ctx, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
+                      uint32_t npoly, float* xy_out) {
+    if (!ctx || !first_point || !xy_out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* dfp = nullptr;
+    int rc = mr_stage_in(ctx, 1, first_point, (size_t)(npoly + 1) * 8, &dfp);
+    if (rc) return rc;
+    void* dout = nullptr;
+    bool st = false;
+    size_t bytes = 0;
+    if (!mr_is_device_ptr(xy_out)) {
+        if (mr_is_device_ptr(first_point)) return mr_fail(ctx, MR_E_BADARG, "synth_polygons: host xy_out needs host first_point");
+        bytes = (size_t)(first_point[npoly] - first_point[0]) * 8;
+    }
+    rc = mr_stage_out(ctx, 0, xy_out, bytes, &dout, &st);
+    if (rc) return rc;
+    rc = mr_synth_polygons_impl(ctx, seed, poly_index0, static_cast<const uint64_t*>(dfp), npoly, static_cast<float*>(dout));
+    if (rc) return rc;
+    if (st) {
+        rc = mr_copy_back(ctx, xy_out, dout, bytes);
+        if (rc) return rc;
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MR_OK;
+}
+
+int mr_ipc_export(mr_context* ctx, void* dev, unsigned char handle_out[MR_IPC_HANDLE_BYTES]) {
+    if (!ctx || !dev || !handle_out) return MR_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) <= MR_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    MR_CUDA(ctx, cudaIpcGetMemHandle(&h, dev));
+    memset(handle_out, 0, MR_IPC_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    return MR_OK;
+}
+int mr_ipc_open(mr_context* ctx, const unsigned char handle[MR_IPC_HANDLE_BYTES], void** dev_out) {
+    if (!ctx || !handle || !dev_out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    MR_CUDA(ctx, cudaIpcOpenMemHandle(dev_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return MR_OK;
+}
+int mr_ipc_close(mr_context* ctx, void* dev) {
+    if (!ctx || !dev) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaIpcCloseMemHandle(dev));
+    return MR_OK;
+}
+
+// Contiguous split of polygons over ranks, balanced by the cost model w(n) = n*log2(n) + n
+// (descent work of the trapezoidation) -- SURVEY 8-e.
+int mr_polygon_partition(const uint64_t* first_point, uint32_t npoly, uint32_t nranks, uint32_t* range_out) {
+    if (!first_point || !range_out || nranks == 0) return MR_E_BADARG;
+    std::vector<double> acc((size_t)npoly + 1, 0.0);
+    for (uint32_t i = 0; i < npoly; ++i) {
+        const double n = (double)(first_point[i + 1] - first_point[i]);
+        const double w = n > 1.0 ? n * std::log2(n) + n : 1.0;
+        acc[i + 1] = acc[i] + w;
+    }
+    const double total = acc[npoly];
+    range_out[0] = 0;
+    uint32_t cur = 0;
+    for (uint32_t r = 1; r < nranks; ++r) {
+        const double target = total * (double)r / (double)nranks;
+        while (cur < npoly && acc[cur + 1] <= target) ++cur;
+        range_out[r] = cur;
+    }
+    range_out[nranks] = npoly;
+    return MR_OK;
+}
+
+int mr_terrain_partition(uint32_t n, uint32_t nranks, uint32_t* rows_out, uint32_t* qrows_out) {
+    if (n == 0 || nranks == 0) return MR_E_BADARG;
+    for (uint32_t r = 0; r <= nranks; ++r) {
+        if (rows_out) rows_out[r] = (uint32_t)((uint64_t)n * r / nranks);
+        if (qrows_out) qrows_out[r] = (uint32_t)((uint64_t)(n - 1) * r / nranks);
+    }
+    return MR_OK;
+}
+
+}  // extern "C"

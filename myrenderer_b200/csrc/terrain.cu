@@ -21,7 +21,7 @@ constexpr int TV_ROWS = 8;       // rows per tile
 struct TerrainArgs {
     const void* height;
     uint32_t n;
-    uint32_t height_row0;
+    uint32_t height_row0, height_rows;  // rows of the heightmap present at `height`
     uint32_t row_begin, row_end;
     unsigned char* vtx_out;  // already offset so that row `row_begin` of the band is addressable
     uint32_t vtx_row0;
@@ -58,19 +58,24 @@ __global__ void __launch_bounds__(TV_THREADS) terrain_vertices_k(const TerrainAr
     const uint32_t tid = threadIdx.x;
 
     // ---- stage the (TV_ROWS+2) x (TV_THREADS+2) height tile, clamped at the borders ----
+    // Rows are clamped to the terrain (central differences are one-sided at the border) and to the
+    // rows the caller provided (a band-local buffer holds only the band plus its halo; rows beyond
+    // it belong to tile rows past row_end, which are never emitted).
+    const int64_t r_lo = a.height_row0;
+    const int64_t r_hi = min((int64_t)n, (int64_t)a.height_row0 + a.height_rows) - 1;
     {
         const uint32_t c = min(c0 + tid, n - 1);
 #pragma unroll
         for (int rr = 0; rr < TV_ROWS + 2; ++rr) {
             int64_t r = (int64_t)r0 + rr - 1;
-            r = r < 0 ? 0 : (r > (int64_t)n - 1 ? (int64_t)n - 1 : r);
+            r = r < r_lo ? r_lo : (r > r_hi ? r_hi : r);
             tile[rr][tid + 1] = load_height<U16>(a.height, (size_t)((uint32_t)r - a.height_row0) * n + c);
         }
         if (tid < 2 * (TV_ROWS + 2)) {
             const int rr = tid >> 1;
             const int side = tid & 1;
             int64_t r = (int64_t)r0 + rr - 1;
-            r = r < 0 ? 0 : (r > (int64_t)n - 1 ? (int64_t)n - 1 : r);
+            r = r < r_lo ? r_lo : (r > r_hi ? r_hi : r);
             int64_t cc = side ? (int64_t)c0 + TV_THREADS : (int64_t)c0 - 1;
             cc = cc < 0 ? 0 : (cc > (int64_t)n - 1 ? (int64_t)n - 1 : cc);
             tile[rr][side ? TV_THREADS + 1 : 0] =
@@ -218,6 +223,7 @@ int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* j) {
         a.height = j->height;
         a.n = n;
         a.height_row0 = j->height_row0;
+        a.height_rows = j->height_rows;
         a.row_begin = j->row_begin;
         a.row_end = j->row_end;
         a.vtx_out = static_cast<unsigned char*>(j->vtx_out);

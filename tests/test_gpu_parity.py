@@ -1,0 +1,395 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle, bit for bit.
+
+Bars (north-star): index buffers, triangulation output and positions bit-exact; normals within
+2 ulp (they are in fact bit-exact: every operation is a single IEEE operation on both sides).
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _ulp_diff(a: np.ndarray, b: np.ndarray) -> int:
+    """max distance in units in the last place between two f32 arrays (finite values)."""
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return int(np.abs(ia - ib).max()) if ia.size else 0
+
+
+def _check_terrain(ctx, oracle, h, n, layout_fields=None, order="decl"):
+    import myrenderer_b200 as mr
+
+    lay = mr.VertexLayout.create(layout_fields or mr.TerrainVertex, order)
+    mesh = mr.Terrain(ctx, lay).create_terrain(h)
+    ctx.sync()
+    olay = (lay.stride, lay.attributes)
+    ovtx, oidx = oracle.terrain_build(h, n, layout=olay, nthreads=0)
+    gv = mesh.vertex_buffer.vertex_buffer.cpu().numpy()
+    gi = mesh.index_buffer.cpu().numpy().view(np.uint32)[: len(oidx)]
+    assert np.array_equal(gi, oidx), "index buffer differs"
+    V = gv.reshape(n * n, lay.stride)
+    Ov = ovtx.reshape(n * n, lay.stride)
+    po = lay.attributes[0][0]
+    assert np.array_equal(V[:, po:po + 12], Ov[:, po:po + 12]), "positions differ"
+    if len(lay.attributes) > 1:
+        no = lay.attributes[1][0]
+        d = _ulp_diff(np.ascontiguousarray(V[:, no:no + 12]).view(np.float32),
+                      np.ascontiguousarray(Ov[:, no:no + 12]).view(np.float32))
+        assert d <= 2, f"normals differ by {d} ulp (tolerance 2 ulp)"
+    assert np.array_equal(gv, ovtx), "vertex bytes (incl. padding) differ"
+    return mesh
+
+
+def test_terrain_reference_heightmap(ctx, oracle):
+    """Config 1: the reference's own 100x100 HEIGHTMAP.png."""
+    h = np.load(os.path.join(GOLDEN, "heightmap_100.npy"))
+    mesh = _check_terrain(ctx, oracle, h, 100)
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))["terrain_100"]
+    gv = mesh.vertex_buffer.vertex_buffer.cpu().numpy()
+    gi = mesh.index_buffer.cpu().numpy().view(np.uint32)
+    assert hashlib.sha256(gv.tobytes()).hexdigest() == kat["vtx_sha256"]
+    assert hashlib.sha256(gi.tobytes()).hexdigest() == kat["idx_sha256"]
+    assert mesh.index_count == 58806 and mesh.vertex_buffer.vertex_count == 10000
+    assert mesh.bounding_box_p0 == (-10.0, 0.0, -10.0) and mesh.bounding_box_p1 == (10.0, 5.0, 10.0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 255, 256, 257, 300, 1000])
+def test_terrain_sizes_u16(ctx, oracle, n):
+    h = oracle.synth_heightmap_u16(0x5EED0001, n)
+    _check_terrain(ctx, oracle, h, n)
+
+
+def test_terrain_f32_heights_and_extremes(ctx, oracle):
+    n = 130
+    h16 = oracle.synth_heightmap_u16(7, n)
+    h16[0, :] = 0
+    h16[1, :] = 65535
+    h16[:, 5] = 65535
+    _check_terrain(ctx, oracle, h16, n)
+    _check_terrain(ctx, oracle, oracle.heightmap_normalize(h16), n)
+
+
+def test_terrain_layout_variants(ctx, oracle):
+    import myrenderer_b200 as mr
+
+    n = 70
+    h = oracle.synth_heightmap_u16(11, n)
+    _check_terrain(ctx, oracle, h, n, (("normal", "Vec3"), ("pos", "Vec3")))  # fast path, swapped slots
+    # generic path: position only (Vec4 slot), and a 48-byte vertex
+    lay = mr.VertexLayout(16, ((0, 3),))
+    mesh = mr.Terrain(ctx, lay).create_terrain(h)
+    ctx.sync()
+    ovtx, _ = oracle.terrain_build(h, n, layout=(16, ((0, 3),)))
+    assert np.array_equal(mesh.vertex_buffer.vertex_buffer.cpu().numpy(), ovtx)
+    lay = mr.VertexLayout(48, ((4, 3), (32, 3)))
+    mesh = mr.Terrain(ctx, lay).create_terrain(h)
+    ctx.sync()
+    ovtx, _ = oracle.terrain_build(h, n, layout=(48, ((4, 3), (32, 3))))
+    assert np.array_equal(mesh.vertex_buffer.vertex_buffer.cpu().numpy(), ovtx)
+
+
+def test_terrain_positions_match_shader_stream(ctx, oracle):
+    """Expanding the indexed mesh reproduces the WGSL vertex stream (Terrain.zig:24-48) bit for bit
+    for every quad with r < n-1 and c < n-1 (SURVEY 8-a2')."""
+    import myrenderer_b200 as mr
+
+    n = 37
+    h16 = oracle.synth_heightmap_u16(3, n)
+    hf = oracle.heightmap_normalize(h16)
+    mesh = mr.Terrain(ctx).create_terrain(h16)
+    ctx.sync()
+    V = mesh.vertex_buffer.vertex_buffer.cpu().numpy().reshape(n * n, 32)[:, :12].copy().view(np.float32)
+    idx = mesh.index_buffer.cpu().numpy().view(np.uint32)
+    k = 0
+    for r in range(n - 1):
+        for c in range(n - 1):
+            quad = r * n + c
+            for corner in range(6):
+                want = oracle.terrain_shader_vertex(hf, n, quad * 6 + corner)
+                got = V[idx[k]]
+                assert want is not None and np.array_equal(got.view(np.uint32), want[:3].view(np.uint32))
+                k += 1
+    assert k == len(idx)
+
+
+def test_terrain_row_band_sharding_matches_unsharded(ctx, oracle):
+    """Logical ranks on one GPU: bands with a 1-row halo and band-local height buffers reproduce the
+    unsharded mesh byte for byte."""
+    import myrenderer_b200 as mr
+
+    torch = _torch()
+    n, G = 203, 4
+    h = oracle.synth_heightmap_u16(0x5EED0004, n)
+    ovtx, oidx = oracle.terrain_build(h, n)
+    T = mr.Terrain(ctx)
+    vtx = torch.zeros(n * n * 32, dtype=torch.uint8, device="cuda")
+    idx = torch.zeros(6 * (n - 1) * (n - 1), dtype=torch.int32, device="cuda")
+    rows = (C.c_uint32 * (G + 1))()
+    qrows = (C.c_uint32 * (G + 1))()
+    assert ctx.lib.mr_terrain_partition(n, G, rows, qrows) == 0
+    for g in range(G):
+        r0, r1 = rows[g], rows[g + 1]
+        lo, hi = max(r0 - 1, 0), min(r1 + 1, n)
+        band = torch.from_numpy(h[lo:hi].copy().view(np.int16)).cuda()  # band + halo only
+        T.build(T.job(band, n, rows=(r0, r1), qrows=(qrows[g], qrows[g + 1]), height_row0=lo,
+                      height_rows=hi - lo, vtx_out=vtx, vtx_row0=0, idx_out=idx, idx_qrow0=0))
+    ctx.sync()
+    assert np.array_equal(vtx.cpu().numpy(), ovtx)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32), oidx)
+    # band-local output buffers (vtx_row0 = row_begin)
+    g = 2
+    r0, r1 = rows[g], rows[g + 1]
+    local = torch.zeros((r1 - r0) * n * 32, dtype=torch.uint8, device="cuda")
+    lidx = torch.zeros((qrows[g + 1] - qrows[g]) * 6 * (n - 1), dtype=torch.int32, device="cuda")
+    hd = torch.from_numpy(h.view(np.int16)).cuda()
+    T.build(T.job(hd, n, rows=(r0, r1), qrows=(qrows[g], qrows[g + 1]), vtx_out=local, vtx_row0=r0,
+                  idx_out=lidx, idx_qrow0=qrows[g]))
+    ctx.sync()
+    assert np.array_equal(local.cpu().numpy(), ovtx[r0 * n * 32: r1 * n * 32])
+    assert np.array_equal(lidx.cpu().numpy().view(np.uint32), oidx[qrows[g] * 6 * (n - 1): qrows[g + 1] * 6 * (n - 1)])
+
+
+def test_terrain_host_pointers(ctx, oracle):
+    """The reference-facing call: host buffers in, host buffers out (copies inside the call)."""
+    import myrenderer_b200 as mr
+
+    n = 90
+    h = oracle.synth_heightmap_u16(5, n)
+    vtx = np.zeros(n * n * 32, dtype=np.uint8)
+    idx = np.zeros(6 * (n - 1) * (n - 1), dtype=np.uint32)
+    T = mr.Terrain(ctx)
+    T.build(T.job(h, n, vtx_out=vtx, idx_out=idx))
+    ovtx, oidx = oracle.terrain_build(h, n)
+    assert np.array_equal(vtx, ovtx) and np.array_equal(idx, oidx)
+
+
+def test_terrain_full_size_4096(ctx, oracle):
+    """Config 2 at full size, compared with the (multi-threaded) oracle byte for byte."""
+    n = 4096
+    h = oracle.synth_heightmap_u16(0x5EED0001, n)
+    _check_terrain(ctx, oracle, h, n)
+
+
+def test_heightmap_normalize(ctx, oracle):
+    torch = _torch()
+    v = np.arange(65536, dtype=np.uint16)
+    out = torch.empty(65536, dtype=torch.float32, device="cuda")
+    d = torch.from_numpy(v.view(np.int16)).cuda()
+    ctx.check(ctx.lib.mr_heightmap_normalize(ctx.handle, d.data_ptr(), 65536, out.data_ptr()), "normalize")
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), oracle.heightmap_normalize(v).view(np.uint32))
+
+
+# ---- polygons ---------------------------------------------------------------------------------
+def _check_batch(ctx, oracle, xy, fp, *, offset_prime=None, seed=0, poly_index0=0, order="decl"):
+    import myrenderer_b200 as mr
+
+    lay = mr.VertexLayout.create(mr.GPUVertex, order)
+    b = mr.Polygon(ctx, lay).create_polygons(xy, fp, offset_prime=offset_prime, seed=seed,
+                                             poly_index0=poly_index0)
+    ctx.sync()
+    ref = oracle.polygon_batch(xy, fp, offset_prime=offset_prime, seed=seed, poly_index0=poly_index0,
+                               layout=(lay.stride, lay.attributes), nthreads=0)
+    gs = b.status.cpu().numpy().view(np.uint32)
+    bad = np.where(gs != ref["status"])[0]
+    assert bad.size == 0, f"status differs at {bad[:5]}: gpu {gs[bad[:5]]} oracle {ref['status'][bad[:5]]}"
+    assert np.array_equal(b.ntri.cpu().numpy().view(np.uint32), ref["ntri"])
+    gv = b.vertex_buffer.cpu().numpy()
+    if not np.array_equal(gv, ref["vtx"]):
+        per = lay.stride * 3
+        ft = ref["first_tri"]
+        for i in range(len(fp) - 1):
+            a, z = int(ft[i]) * per, int(ft[i + 1]) * per
+            assert np.array_equal(gv[a:z], ref["vtx"][a:z]), f"vertices of polygon {i} (n={int(fp[i+1]-fp[i])}) differ"
+    gb = b.bbox.cpu().numpy().view(np.uint32)
+    assert np.array_equal(gb, ref["bbox"].view(np.uint32)), "bbox differs"
+    return b, ref
+
+
+def test_app_polygons_all_orders(ctx, oracle):
+    """Config 1: the two literal polygons of App.zig:68-83 for every (offset, prime), against the
+    committed known answers."""
+    app = json.load(open(os.path.join(GOLDEN, "app_polygons.json")))
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    for name in ("polygon1", "polygon2"):
+        p = np.array(app[name], dtype=np.float32)
+        keys = sorted(kat[name].keys())
+        ops = np.array([[int(x) for x in k.split(",")] for k in keys], dtype=np.uint32)
+        xy = np.tile(p, (len(keys), 1))
+        fp = np.arange(len(keys) + 1, dtype=np.uint64) * len(p)
+        b, ref = _check_batch(ctx, oracle, xy, fp, offset_prime=ops)
+        gv = b.vertex_buffer.cpu().numpy()
+        per = 96 * (len(p) - 2)
+        for i, k in enumerate(keys):
+            assert hashlib.sha256(gv[i * per:(i + 1) * per].tobytes()).hexdigest() == kat[name][k]["vtx_sha256"]
+            assert int(b.status.cpu().numpy()[i]) == kat[name][k]["status"]
+
+
+def test_known_answer_square_linear_order(ctx):
+    """SURVEY 8-a hand-derived: polygon2 with (offset 0, prime 1) emits (2,3,1),(3,0,1)."""
+    import myrenderer_b200 as mr
+
+    sq = np.array([[10, 10], [40, 10], [40, 40], [10, 40]], dtype=np.float32)
+    got = []
+    st = mr.Triangulation(ctx).create_polygon(sq, got, lambda c, p: c.append(p), offset_prime=(0, 1))
+    assert st == 0
+    assert got == [(40.0, 40.0), (10.0, 40.0), (40.0, 10.0), (10.0, 40.0), (10.0, 10.0), (40.0, 10.0)]
+    obj = mr.Polygon(ctx).create_polygon(sq, offset_prime=(0, 1))
+    raw = obj.vertex_buffer.vertex_buffer.cpu().numpy().reshape(6, 32)
+    col = raw[:, 16:28].copy().view(np.uint32).reshape(6, 3)
+    assert col[0].tolist() == [0x3EB6B6B7, 0x3E44C4C5, 0x3EBCBCBD]  # palette[0], Polygon.zig:67
+    assert col[3].tolist() == [0x3EE0E0E1, 0x3F800000, 0x3F4FCFD0]  # palette[1]
+    assert obj.bounding_box_p0 == (0.0, 0.0, 0.0) and obj.bounding_box_p1 == (40.0, 40.0, 0.0)
+
+
+def test_star_polygons_seeded(ctx, oracle):
+    """Config 3 shape at reduced count: star polygons n in [8,64], device-seeded unirand.  Covers every
+    status the reference algorithm produces on such input (OK, overflow, underfill, null unwrap)."""
+    seed = 0x5EED0003
+    fp = oracle.synth_polygon_sizes(seed, 4000, 8, 64)
+    xy = oracle.synth_polygons(seed, fp)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=seed)
+    seen = set(np.unique(ref["status"]).tolist())
+    assert 0 in seen and any(s & 4 for s in seen) and any(s & 8 for s in seen)
+
+
+def test_zigauto_layout_and_index_offset(ctx, oracle):
+    seed = 99
+    fp = oracle.synth_polygon_sizes(seed, 300, 3, 40)
+    xy = oracle.synth_polygons(seed, fp)
+    _check_batch(ctx, oracle, xy, fp, seed=seed, poly_index0=12345, order="zigauto")
+
+
+def test_convex_and_large_polygons(ctx, oracle):
+    """Sizes up to 1024 (every shared-memory class) and 1025..4096 (global-memory tier)."""
+    rng = np.random.default_rng(5)
+    sizes = [3, 4, 5, 16, 17, 32, 33, 64, 65, 128, 129, 256, 257, 512, 513, 1024, 1025, 2000, 4096]
+    pts = []
+    for n in sizes:
+        th = 2 * np.pi * (np.arange(n) + 0.8 * rng.random(n) - 0.4) / n
+        a, b, ph = 40 + 50 * rng.random(), 40 + 50 * rng.random(), rng.random() * 6.28
+        x, y = a * np.cos(th), b * np.sin(th)
+        pts.append(np.stack([100 + np.cos(ph) * x - np.sin(ph) * y, 100 + np.sin(ph) * x + np.cos(ph) * y], 1))
+    xy = np.concatenate(pts).astype(np.float32)
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=1)
+    assert (ref["status"] == 0).all(), "the reference algorithm handles convex polygons"
+
+
+def test_skewed_sizes_loguniform(ctx, oracle):
+    """Config 5 shape at reduced count: log-uniform sizes 8..1024, star-shaped (mostly failing in the
+    reference algorithm -> exercises arena caps and re-queueing to the global-memory tier)."""
+    seed = 0x5EED0005
+    fp = oracle.synth_polygon_sizes(seed, 400, 8, 1024, dist=1)
+    xy = oracle.synth_polygons(seed, fp)
+    _check_batch(ctx, oracle, xy, fp, seed=seed)
+
+
+def test_edge_cases(ctx, oracle):
+    polys = [
+        np.zeros((0, 2)),                                     # empty
+        np.array([[1, 1]]),                                   # n = 1
+        np.array([[1, 1], [2, 2]]),                           # n = 2
+        np.array([[0, 0], [10, 0], [0, 10]]),                 # triangle
+        np.array([[0, 0], [10, 0], [np.nan, 10], [0, 5]]),    # NaN
+        np.array([[0, 0], [np.inf, 0], [5, 10], [0, 5]]),     # Inf
+        np.array([[0, 0], [5, 0], [10, 0], [10, 10], [0, 10]]),       # collinear run on a horizontal edge
+        np.array([[0, 0], [10, 0], [10, 0], [10, 10], [0, 10]]),      # coincident consecutive points
+        np.array([[5, 5], [5, 5], [5, 5], [5, 5]]),                   # all coincident
+        np.array([[0, 0], [10, 10], [10, 0], [0, 10]]),               # self-intersecting (bow tie)
+        np.array([[10, 10], [10, 40], [40, 40], [40, 10]]),           # square, opposite orientation
+        np.array([[0, 0], [2e10, 5e-41], [1e10, 1e-40]]),             # atan2 corner: pi vs 0 (not acute)
+        np.array([[0, 0], [3e38, 0], [3e38, 3e38], [-3e38, 3e38]]),   # differences overflow to inf
+    ]
+    xy = np.concatenate([p.reshape(-1, 2) for p in polys]).astype(np.float32)
+    fp = np.concatenate([[0], np.cumsum([len(p) for p in polys])]).astype(np.uint64)
+    for seed in (1, 2, 3):
+        _, ref = _check_batch(ctx, oracle, xy, fp, seed=seed)
+    assert ref["status"][0] == 1 and ref["status"][1] == 1 and ref["status"][2] == 1
+    assert ref["status"][4] == 2 and ref["status"][5] == 2
+
+
+def test_too_large_polygon(ctx, oracle):
+    n = 4097
+    th = 2 * np.pi * np.arange(n) / n
+    xy = np.stack([100 + 50 * np.cos(th), 100 + 50 * np.sin(th)], 1).astype(np.float32)
+    xy = np.concatenate([xy, np.array([[0, 0], [10, 0], [0, 10]], dtype=np.float32)])
+    fp = np.array([0, n, n + 3], dtype=np.uint64)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=1)
+    assert ref["status"][0] == 32 and ref["status"][1] == 0
+
+
+def test_polygon_host_pointers_and_subrange(ctx, oracle):
+    """Host buffers through the C ABI; and a sub-batch [a,b) addressed with point_base / tri_base
+    (the per-rank call of the sharded path)."""
+    import myrenderer_b200 as mr
+
+    seed = 21
+    fp = oracle.synth_polygon_sizes(seed, 200, 5, 50)
+    xy = oracle.synth_polygons(seed, fp)
+    ref = oracle.polygon_batch(xy, fp, seed=seed)
+    ft = ref["first_tri"]
+    P = mr.Polygon(ctx)
+    vtx = np.zeros(int(ft[-1]) * 96, dtype=np.uint8)
+    status = np.zeros(200, dtype=np.uint32)
+    ntri = np.zeros(200, dtype=np.uint32)
+    bbox = np.zeros((200, 4), dtype=np.float32)
+    for a, z in ((0, 77), (77, 200)):  # two "ranks" writing into one buffer
+        j = P.job(xy, fp[a:z + 1].copy(), z - a, vtx_out=vtx, first_tri=ft[a:z + 1].copy(), bbox_out=bbox[a:z],
+                  status_out=status[a:z], ntri_out=ntri[a:z], seed=seed, poly_index0=a)
+        P.triangulate(j)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(ntri, ref["ntri"])
+    assert np.array_equal(vtx, ref["vtx"]) and np.array_equal(bbox.view(np.uint32), ref["bbox"].view(np.uint32))
+
+
+def test_unirand_device_port(ctx, oracle):
+    torch = _torch()
+    tops = np.concatenate([np.arange(2, 300), [509, 521, 1013, 1024, 1723, 1724, 4096]])
+    fp = np.concatenate([[0], np.cumsum(tops)]).astype(np.uint64)
+    out = torch.empty(2 * len(tops), dtype=torch.int32, device="cuda")
+    d = torch.from_numpy(fp.view(np.int64)).cuda()
+    ctx.check(ctx.lib.mr_unirand_seed_batch(ctx.handle, d.data_ptr(), len(tops), 0xABCDEF, 7, out.data_ptr()), "seed")
+    ctx.sync()
+    got = out.cpu().numpy().view(np.uint32).reshape(-1, 2)
+    for i, t in enumerate(tops):
+        assert tuple(got[i]) == oracle.unirand_seed(int(t), 0xABCDEF, 7 + i)
+
+
+def test_synth_generators_match_host_definition(ctx, oracle):
+    torch = _torch()
+    n = 257
+    out = torch.empty(n * n, dtype=torch.int16, device="cuda")
+    ctx.check(ctx.lib.mr_synth_heightmap_u16(ctx.handle, 0x5EED0001, n, 0, n, out.data_ptr()), "synth h")
+    fp = oracle.synth_polygon_sizes(0x5EED0003, 3000, 8, 64)
+    d = torch.from_numpy(fp.view(np.int64)).cuda()
+    xy = torch.empty(int(fp[-1]) * 2, dtype=torch.float32, device="cuda")
+    ctx.check(ctx.lib.mr_synth_polygons(ctx.handle, 0x5EED0003, 0, d.data_ptr(), 3000, xy.data_ptr()), "synth p")
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint16).reshape(n, n), oracle.synth_heightmap_u16(0x5EED0001, n))
+    want = oracle.synth_polygons(0x5EED0003, fp)
+    assert np.array_equal(xy.cpu().numpy().view(np.uint32), want.reshape(-1).view(np.uint32))
+
+
+def test_polygon_offsets_device(ctx, oracle):
+    torch = _torch()
+    fp = oracle.synth_polygon_sizes(4, 5000, 1, 70)
+    d = torch.from_numpy(fp.view(np.int64)).cuda()
+    out = torch.empty(5001, dtype=torch.int64, device="cuda")
+    ctx.check(ctx.lib.mr_polygon_offsets(ctx.handle, d.data_ptr(), 5000, out.data_ptr()), "offsets")
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), oracle.polygon_offsets(fp))
