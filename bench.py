@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- the geometry hot path on N B200s of one node.
+
+One *step* = one pass of the hot path over one batch of synthetic input:
+    terrain   n x n hash-noise u16 heightmap  ->  vertices (pos + normal, 32 B) + u32 index buffer
+    polygons  star-shaped simple polygons, 8..64 vertices, device-seeded unirand edge order
+At N=1 the workload is BASELINE.json configs[1] + configs[2]: n = 4096 and 100,000 polygons
+(SURVEY 8-d configs 2 and 3).  At N>1 the work is sharded with no data-path collective (weak
+scaling): the terrain becomes an n_G x n_G heightmap with n_G = round(4096*sqrt(N)) cut into N
+row bands with a one-row halo, the polygon batch becomes 100,000*N polygons cut into N
+cost-balanced contiguous ranges; every rank produces its shard into its own HBM.
+
+Headline `value` = terrain Mverts/s (unique grid vertices produced per second, vertices + normals +
+indices all written), inputs resident in HBM.  The polygon throughput of the same steps is in
+"polygons".  `e2e` is the same terrain metric through the reference-facing C-ABI call with pinned
+HOST buffers (H2D of the heightmap and D2H of vertices + indices inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TERRAIN_N1 = 4096
+POLYS_PER_GPU = 100_000
+SEED_TERRAIN = 0x5EED0001
+SEED_POLY = 0x5EED0003
+POLY_NMIN, POLY_NMAX = 8, 64
+STRIDE = 32
+
+
+def terrain_size(world: int) -> int:
+    return int(round(TERRAIN_N1 * world ** 0.5))
+
+
+def terrain_bytes(n: int, rows: int, qrows: int):
+    """Algorithmic bytes (SURVEY 8-d, u16 conversion fused so the read term is 2 B/texel)."""
+    return 2 * rows * n + STRIDE * rows * n, 24 * qrows * (n - 1)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rates(world: int, nthreads: int, budget_polys: int = 200_000):
+    """Times the CPU oracle (C restatement of the Zig source, prints removed) on a bounded sample of
+    the N-GPU workload.  Returns rates + a description.  Only called for cpu_baseline / --impl reference."""
+    from oracle import oracle as O
+
+    n = terrain_size(world)
+    rows = min(n, max(1, (TERRAIN_N1 * TERRAIN_N1) // n))  # ~one GPU's share of rows
+    lo, hi = 0, min(n, rows + 1)
+    h = O.synth_heightmap_u16(SEED_TERRAIN, n, 0, hi - lo)
+    t0 = time.perf_counter()
+    O.terrain_build(h, n, rows=(0, rows), qrows=(0, min(rows, n - 1)), nthreads=nthreads)
+    t_terrain = time.perf_counter() - t0
+    npoly = min(POLYS_PER_GPU * world, budget_polys)
+    fp = O.synth_polygon_sizes(SEED_POLY, npoly, POLY_NMIN, POLY_NMAX)
+    xy = O.synth_polygons(SEED_POLY, fp)
+    t0 = time.perf_counter()
+    O.polygon_batch(xy, fp, seed=SEED_POLY, nthreads=nthreads, want_ids=False)
+    t_poly = time.perf_counter() - t0
+    return {
+        "terrain_mverts_per_s": rows * n / t_terrain / 1e6,
+        "polygons_per_s": npoly / t_poly,
+        "terrain_s": t_terrain, "polygons_s": t_poly,
+        "sample": f"terrain rows [0,{rows}) of a {n}x{n} heightmap (vertices+normals+indices); "
+                  f"first {npoly} polygons of the batch",
+    }
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Zig reference cannot
+    be built here (no Zig toolchain, un-vendored deps), so this is the C restatement (oracle port)
+    with debug prints removed, on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    T = O.hardware_threads()
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_rates(args.gpus, T, budget_polys=20_000)
+    ts, tp, last = [], [], None
+    for _ in range(args.steps):
+        last = cpu_reference_rates(args.gpus, T)
+        ts.append(last["terrain_mverts_per_s"])
+        tp.append(last["polygons_per_s"])
+    val = statistics.mean(ts)
+    line = {
+        "impl": "reference", "metric": "terrain_mverts_per_s", "value": val, "unit": "Mverts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (last["terrain_s"] + last["polygons_s"]), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus)},
+        "polygons": {"value": statistics.mean(tp), "unit": "polygons/s"},
+        "cpu_baseline": {"value": val, "unit": "Mverts/s", "cores": T, "kind": "port",
+                         "sample": last["sample"], "polygons_per_s": statistics.mean(tp),
+                         "note": "CPU = C restatement of the Zig source (oracle/), not the Zig binary"},
+        "e2e": {"value": val, "unit": "Mverts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(world: int) -> str:
+    n = terrain_size(world)
+    return (f"terrain {n}x{n} u16 hash-noise heightmap -> pos+normal vertices (32 B) + u32 indices, "
+            f"row-band sharded x{world}; {POLYS_PER_GPU * world} star polygons n in [{POLY_NMIN},{POLY_NMAX}], "
+            f"cost-balanced x{world}")
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import myrenderer_b200 as mr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    dev = torch.device("cuda", local)
+    ctx = mr.Context(local)  # runs on torch's current stream
+    lib = ctx.lib
+    T = mr.Terrain(ctx)
+    P = mr.Polygon(ctx)
+
+    # ---- this rank's shard ---------------------------------------------------------------------
+    n = terrain_size(world)
+    rows_p = (C.c_uint32 * (world + 1))()
+    qrows_p = (C.c_uint32 * (world + 1))()
+    lib.mr_terrain_partition(n, world, rows_p, qrows_p)
+    r0, r1, q0, q1 = rows_p[rank], rows_p[rank + 1], qrows_p[rank], qrows_p[rank + 1]
+    lo, hi = max(r0 - 1, 0), min(r1 + 1, n)
+    height = torch.empty((hi - lo) * n, dtype=torch.int16, device=dev)  # band + halo, u16
+    ctx.check(lib.mr_synth_heightmap_u16(ctx.handle, SEED_TERRAIN, n, lo, hi - lo, height.data_ptr()), "synth heightmap")
+    vtx = torch.empty((r1 - r0) * n * STRIDE, dtype=torch.uint8, device=dev)
+    idx = torch.empty(max((q1 - q0) * 6 * (n - 1), 1), dtype=torch.int32, device=dev)
+    job_v = T.job(height, n, rows=(r0, r1), qrows=(q0, q0), height_row0=lo, height_rows=hi - lo, vtx_out=vtx, vtx_row0=r0)
+    job_i = T.job(height, n, rows=(r0, r0), qrows=(q0, q1), height_row0=lo, height_rows=hi - lo, idx_out=idx, idx_qrow0=q0)
+
+    npoly_total = POLYS_PER_GPU * world
+    fp_all = np.zeros(npoly_total + 1, dtype=np.uint64)
+    lib.mr_synth_polygon_sizes(SEED_POLY, 0, npoly_total, POLY_NMIN, POLY_NMAX, 0, fp_all.ctypes.data)
+    ranges = (C.c_uint32 * (world + 1))()
+    lib.mr_polygon_partition(fp_all.ctypes.data, npoly_total, world, ranges)
+    pa, pb = ranges[rank], ranges[rank + 1]
+    fp = np.ascontiguousarray(fp_all[pa:pb + 1])
+    ft = mr.polygon_offsets_host(fp)  # local triangle offsets
+    npoly, npts, ntri = pb - pa, int(fp[-1] - fp[0]), int(ft[-1])
+    fp_d = torch.from_numpy(fp.view(np.int64)).to(dev)
+    ft_d = torch.from_numpy(ft.view(np.int64)).to(dev)
+    xy = torch.empty(npts * 2, dtype=torch.float32, device=dev)
+    ctx.check(lib.mr_synth_polygons(ctx.handle, SEED_POLY, pa, fp_d.data_ptr(), npoly, xy.data_ptr()), "synth polygons")
+    pvtx = torch.empty(ntri * 3 * STRIDE, dtype=torch.uint8, device=dev)
+    pbbox = torch.empty(npoly * 4, dtype=torch.float32, device=dev)
+    pstat = torch.empty(npoly, dtype=torch.int32, device=dev)
+    pntri = torch.empty(npoly, dtype=torch.int32, device=dev)
+    job_p = P.job(xy, fp_d, npoly, vtx_out=pvtx, first_tri=ft_d, bbox_out=pbbox, status_out=pstat, ntri_out=pntri,
+                  seed=SEED_POLY, poly_index0=pa, point_base=int(fp[0]))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 2x L2
+    ctx.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(timers=None):
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        T.build(job_v)
+        e1.record()
+        T.build(job_i)
+        e2.record()
+        P.triangulate(job_p)
+        e3.record()
+        if timers is not None:
+            timers.append((e0, e1, e2, e3))
+
+    for _ in range(args.warmup):
+        step()
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.launch_count
+    timers = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(timers)
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step event pairs)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    tv = [a.elapsed_time(b) for a, b, _, _ in timers]
+    ti = [b.elapsed_time(c) for _, b, c, _ in timers]
+    tp = [c.elapsed_time(d) for _, _, c, d in timers]
+    ms_v, ms_i, ms_p = (sum(x) / len(x) for x in (tv, ti, tp))
+
+    # ---- end to end through the C ABI with pinned host buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_height = torch.empty((hi - lo) * n, dtype=torch.int16, pin_memory=True)
+        h_height.copy_(height)
+        h_vtx = torch.empty((r1 - r0) * n * STRIDE, dtype=torch.uint8, pin_memory=True)
+        h_idx = torch.empty(max((q1 - q0) * 6 * (n - 1), 1), dtype=torch.int32, pin_memory=True)
+        h_xy = torch.empty(npts * 2, dtype=torch.float32, pin_memory=True)
+        h_xy.copy_(xy)
+        h_pvtx = torch.empty(ntri * 3 * STRIDE, dtype=torch.uint8, pin_memory=True)
+        h_bbox = torch.empty(npoly * 4, dtype=torch.float32, pin_memory=True)
+        h_stat = torch.empty(npoly, dtype=torch.int32, pin_memory=True)
+        h_ntri = torch.empty(npoly, dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+        job_e = T.job(h_height, n, rows=(r0, r1), qrows=(q0, q1), height_row0=lo, height_rows=hi - lo,
+                      vtx_out=h_vtx, vtx_row0=r0, idx_out=h_idx, idx_qrow0=q0)
+        job_pe = P.job(h_xy, fp, npoly, vtx_out=h_pvtx, first_tri=ft, bbox_out=h_bbox, status_out=h_stat,
+                       ntri_out=h_ntri, seed=SEED_POLY, poly_index0=pa, point_base=int(fp[0]))
+        esteps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            T.build(job_e)
+            P.triangulate(job_pe)
+        barrier()
+        te, tpe = [], []
+        for _ in range(esteps):
+            a, b, c = ev(), ev(), ev()
+            a.record()
+            T.build(job_e)   # H2D heightmap -> kernels -> D2H vertices + indices, returns when the host buffers are filled
+            b.record()
+            P.triangulate(job_pe)
+            c.record()
+            torch.cuda.synchronize()
+            te.append(a.elapsed_time(b))
+            tpe.append(b.elapsed_time(c))
+        barrier()
+        e2e = {"ms_terrain": sum(te) / len(te), "ms_polygons": sum(tpe) / len(tpe),
+               "h2d_terrain": h_height.numel() * 2, "d2h_terrain": h_vtx.numel() + h_idx.numel() * 4,
+               "h2d_poly": h_xy.numel() * 4 + fp.nbytes + ft.nbytes,
+               "d2h_poly": h_pvtx.numel() + h_bbox.numel() * 4 + h_stat.numel() * 4 + h_ntri.numel() * 4,
+               "status_ok": int((h_stat.numpy() == 0).sum())}
+
+    # ---- reduce over ranks: max time, sum of units ------------------------------------------------
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    g_ms_v, g_ms_i, g_ms_p = reduce_max(ms_v), reduce_max(ms_i), reduce_max(ms_p)
+    g_ms_terrain = reduce_max(ms_v + ms_i)
+    g_ms_step = reduce_max(ms_v + ms_i + ms_p)
+    verts_total = reduce_sum((r1 - r0) * n)
+    polys_total = reduce_sum(npoly)
+    bv, bi = terrain_bytes(n, r1 - r0, q1 - q0)
+    bytes_terrain_total = reduce_sum(bv + bi)
+    launches_total = int(reduce_sum(launches))
+    if e2e is not None:
+        e_ms_t = reduce_max(e2e["ms_terrain"])
+        e_ms_p = reduce_max(e2e["ms_polygons"])
+        e_h2d = int(reduce_sum(e2e["h2d_terrain"] + e2e["h2d_poly"]))
+        e_d2h = int(reduce_sum(e2e["d2h_terrain"] + e2e["d2h_poly"]))
+    ok_total = reduce_sum(int((pstat == 0).sum().item()))
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = verts_total / (g_ms_terrain * 1e-3) / 1e6
+        achieved_v = bv / (ms_v * 1e-3) / 1e9  # rank 0's dominant kernel
+        line = {
+            "metric": "terrain_mverts_per_s",
+            "value": value, "unit": "Mverts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": g_ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(world), "terrain_n": n, "polygons": int(polys_total),
+                       "l2": "256 MiB buffer written between timed iterations; each step also writes >1.2 GB",
+                       "timing": "CUDA events on the launching stream; value = vertices / (vertex kernel + index kernel) "
+                                 "time, max over ranks; ms_per_step = terrain + polygon kernels"},
+            "terrain": {"ms": g_ms_terrain, "ms_vertices_kernel": g_ms_v, "ms_indices_kernel": g_ms_i,
+                        "achieved_gb_per_s": bytes_terrain_total / (g_ms_terrain * 1e-3) / 1e9,
+                        "algorithmic_bytes": int(bytes_terrain_total)},
+            "polygons": {"value": polys_total / (g_ms_p * 1e-3), "unit": "polygons/s", "ms": g_ms_p,
+                         "status_ok_fraction": ok_total / polys_total,
+                         "note": "star polygons of SURVEY 8-d config 3; the reference algorithm itself fails "
+                                 "(overflow/underfill/null-unwrap) on the non-OK fraction and the kernel reproduces that"},
+            "gpu_launches": launches_total,
+            "wall_s_timed_region": wall,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "terrain_vertices_k", "achieved": achieved_v, "peak": peak,
+                         "unit": "GB/s", "frac": achieved_v / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(bv),
+                         "indices_kernel": {"achieved": bi / (ms_i * 1e-3) / 1e9, "frac": bi / (ms_i * 1e-3) / 1e9 / peak,
+                                            "algorithmic_bytes_per_launch": int(bi)}},
+        }
+        if e2e is not None:
+            line["e2e"] = {"value": verts_total / (e_ms_t * 1e-3) / 1e6, "unit": "Mverts/s",
+                           "h2d_bytes_per_step": e_h2d, "d2h_bytes_per_step": e_d2h, "ms_terrain": e_ms_t,
+                           "ms_polygons": e_ms_p, "polygons_per_s": polys_total / (e_ms_p * 1e-3),
+                           "path": "mr_terrain_build / mr_triangulate_batch with pinned host buffers"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O  # CPU baseline leg only
+
+            Tn = O.hardware_threads()
+            cpu = cpu_reference_rates(1, Tn)
+            cpu1 = cpu_reference_rates(1, 1, budget_polys=20_000)
+            line["cpu_baseline"] = {
+                "value": cpu["terrain_mverts_per_s"], "unit": "Mverts/s", "cores": Tn, "kind": "port",
+                "sample": cpu["sample"], "polygons_per_s": cpu["polygons_per_s"],
+                "single_thread": {"terrain_mverts_per_s": cpu1["terrain_mverts_per_s"],
+                                  "polygons_per_s": cpu1["polygons_per_s"], "sample": cpu1["sample"]},
+                "note": "CPU = C restatement of the Zig source (oracle/), prints removed; not the Zig binary"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,6 +67,8 @@ typedef struct mr_o_stats {
     uint64_t max_mountain;   /* longest mountain list (with duplicates)           */
     uint64_t triangles;      /* triangles emitted                                 */
     uint64_t not_acute;      /* push_triangle_if_acute calls that returned false  */
+    uint64_t point_steps;    /* descent_steps spent in add_point                  */
+    uint64_t select_steps;   /* iterations of the pass-2 selection loop (:329-337) */
 } mr_o_stats;
 
 typedef struct mr_o_tri mr_o_tri; /* reusable arenas, like the Zig struct */

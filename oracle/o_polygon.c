@@ -200,6 +200,8 @@ int mr_o_polygon_batch(const mr_polygon_job* job, uint32_t* ids_out, int nthread
             stats_total->mountains += ws[i].stats.mountains;
             stats_total->triangles += ws[i].stats.triangles;
             stats_total->not_acute += ws[i].stats.not_acute;
+            stats_total->point_steps += ws[i].stats.point_steps;
+            stats_total->select_steps += ws[i].stats.select_steps;
             if (ws[i].stats.max_stack > stats_total->max_stack)
                 stats_total->max_stack = ws[i].stats.max_stack;
             if (ws[i].stats.max_mountain > stats_total->max_mountain)

@@ -128,7 +128,10 @@ static int add_point(mr_o_tri* t, uint32_t point_id) {
     for (;;) { /* :144-167 */
         mr_o_node* nd = &t->nodes[base];
         uint32_t next, p;
-        if (t->stats) t->stats->descent_steps++;
+        if (t->stats) {
+            t->stats->descent_steps++;
+            t->stats->point_steps++;
+        }
         if (nd->type == T_TRAPEZOID) break;
         if (nd->type == T_POINT) {
             if (nd->point1 == point_id) return 1; /* :149-152 already added */
@@ -276,6 +279,7 @@ static int add_segment(mr_o_tri* t, uint32_t point1, uint32_t point2) {
             uint32_t node = t->node_stack[i];
             uint32_t np;
             UNWRAP(np, t->nodes[node].point2);
+            if (t->stats) t->stats->select_steps++;
             if (point_is_above(t, np, low_point)) {
                 low_point = np;
                 base_index = i;

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_DIR, "libmr_oracle.so")
 class OStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in (
         "nodes", "max_stack", "sum_stack", "descent_steps", "mountains", "max_mountain",
-        "triangles", "not_acute")]
+        "triangles", "not_acute", "point_steps", "select_steps")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
