@@ -145,8 +145,9 @@ int mr_fill_zero(mr_context* ctx, void* dev, size_t bytes);
  *       rm=max(r-1,0) rp=min(r+1,n-1) (same for c)
  *       gx = (height_scale*(h[rp][c]-h[rm][c])) / (grid_step*(float)(rp-rm))
  *       gz = (height_scale*(h[r][cp]-h[r][cm])) / (grid_step*(float)(cp-cm))
- *       len = sqrtf(((gx*gx)+1.0f)+(gz*gz));  normal = (-gx/len, 1.0f/len, -gz/len)
- *     IEEE round-to-nearest for every operation, no FMA; n==1 gives gx=gz=0.
+ *       len = sqrtf(((gx*gx)+1.0f)+(gz*gz));  inv = 1.0f/len;  normal = (-gx*inv, inv, -gz*inv)
+ *     IEEE round-to-nearest for every operation, no FMA; n==1 gives gx=gz=0.  (One reciprocal and
+ *     two products instead of three quotients: at most 1 ulp from the quotient form.)
  *   indices [NEW SPEC]: u32, 6 per quad, quads (r,c) r,c in [0,n-1) row-major, corner order of
  *       Terrain.zig:28-35 under cw front faces (Pipeline.zig:145-149):
  *       (r+1,c) (r,c) (r+1,c+1) (r+1,c+1) (r,c) (r,c+1)   with i(r,c)=r*n+c
@@ -189,6 +190,10 @@ int mr_terrain_build_full(mr_context* ctx, const void* height, uint32_t height_f
 /* bounding box + draw descriptor (Terrain.zig:103-110,126 adapted to the indexed mesh) */
 int mr_terrain_describe(uint32_t n, const mr_terrain_params* params, float bbox_min[3],
                         float bbox_max[3], uint64_t* vertex_count, uint64_t* index_count);
+/* Self-test used by the test-suite: compares the kernels' constant-divisor quotient routine with IEEE
+ * division for all 2^32 dividends and returns the number of mismatches (0 expected).  force_fast != 0
+ * exercises the reciprocal-and-correct path even for a divisor the library would not enable it for. */
+int mr_selftest_fastdiv(mr_context* ctx, float divisor, int force_fast, uint64_t* mismatches_out);
 /* Standalone heightmap normalisation (Terrain.zig:114-124): u16 -> f32. */
 int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, float* out);
 

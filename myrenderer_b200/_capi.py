@@ -135,6 +135,7 @@ SIGNATURES = {
          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     ),
     "mr_heightmap_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "mr_selftest_fastdiv": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.POINTER(C.c_uint64)]),
     "mr_triangulate_batch": (C.c_int, [C.c_void_p, C.POINTER(MrPolygonJob)]),
     "mr_polygon_offsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "mr_polygon_draw_range": (

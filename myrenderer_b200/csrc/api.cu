@@ -7,6 +7,7 @@
 #include "unirand.cuh"
 
 int mr_heightmap_normalize_impl(mr_context* ctx, const uint16_t* in, uint64_t count, float* out);
+int mr_selftest_fastdiv_impl(mr_context* ctx, float b, int force_fast, unsigned long long* mismatches_dev);
 int mr_polygon_offsets_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t* first_tri_dev);
 int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t seed,
                                uint64_t poly_index0, uint32_t* out_dev);
@@ -293,6 +294,20 @@ int mr_terrain_build_full(mr_context* ctx, const void* height, uint32_t height_f
     if (layout) j.layout = *layout; else mr_layout_preset(MR_LAYOUT_TERRAINVERTEX, &j.layout);
     if (params) j.params = *params; else mr_terrain_params_default(&j.params);
     return mr_terrain_build(ctx, &j);
+}
+
+int mr_selftest_fastdiv(mr_context* ctx, float divisor, int force_fast, uint64_t* mismatches_out) {
+    if (!ctx || !mismatches_out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* d = nullptr;
+    int rc = mr_scratch(ctx, 10, 8, &d);
+    if (rc) return rc;
+    MR_CUDA(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+    rc = mr_selftest_fastdiv_impl(ctx, divisor, force_fast, static_cast<unsigned long long*>(d));
+    if (rc) return rc;
+    MR_CUDA(ctx, cudaMemcpyAsync(mismatches_out, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MR_OK;
 }
 
 int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, float* out) {

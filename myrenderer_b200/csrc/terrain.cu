@@ -2,41 +2,71 @@
 //
 // Replaces the body of Terrain.create_terrain (Terrain/Terrain.zig:88-129) plus the per-frame WGSL
 // vertex formula (Terrain/Terrain.zig:21-50) with a one-off mesh build:
-//   terrain_vertices_k   streaming stencil: height tile (+1 halo) staged in shared memory as f32
-//                        (u16 -> f32 of Terrain.zig:120 fused into the load), one thread per
-//                        column walking down the tile, one 32-byte STG.256 per vertex
-//                        (position slot + normal slot), 1 KB contiguous per warp store.
-//   terrain_indices_k    closed-form, write-only: one 16-byte store per thread, aligned per row.
+//   terrain_vertices_k   streaming stencil.  A (16+2) x (256+2) height tile is staged in shared memory
+//                        as f32 (the u16 -> f32 of Terrain.zig:120 fused into the load), then one
+//                        thread per column walks down the tile with a rolling 3-row window and emits
+//                        ONE 32-byte store (STG.E.ENL2.256: position slot + normal slot) per vertex,
+//                        i.e. 1 KB contiguous per warp instruction.  HBM-bound by design: 2 B read +
+//                        32 B written per vertex.
+//   terrain_indices_k    closed-form, write-only.  Quads are a linear stream (24 B each); a CTA builds
+//                        1024 quads in shared memory and ships them with one TMA bulk store
+//                        (cp.async.bulk.global.shared::cta -> UBLKCP), so no per-thread store math.
 //   heightmap_normalize_k  standalone Terrain.zig:120.
-// Float rules: every product/difference/quotient is its own IEEE round-to-nearest operation
-// (__fmul_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn are never contracted), so positions are bit-identical
-// to the reference formula evaluated without FMA and normals follow the spec in the header.
+// Float rules: every product/difference/quotient is its own IEEE round-to-nearest operation.  The
+// quotients by the kernel-wide constants 65535, grid_step and 2*grid_step use the exact
+// reciprocal-and-correct scheme  q = a*y; r = fma(-q,b,a); q' = fma(r,y,q)  with y = RN(1/b): for the
+// constants enabled here it returns RN(a/b) for every a in the guarded exponent range (checked
+// exhaustively on the GPU by mr_selftest_fastdiv, tests/test_gpu_parity.py); outside the range, or
+// for other constants, __fdiv_rn is used.  So positions are bit-identical to the reference formula
+// evaluated without FMA contraction and normals follow the spec in the header bit for bit.
 #include "common.cuh"
 
 namespace {
 
 constexpr int TV_THREADS = 256;  // columns per tile
-constexpr int TV_ROWS = 8;       // rows per tile
+constexpr int TV_ROWS = 16;      // rows per tile
+
+struct DivConst {
+    float b;  // divisor
+    float y;  // RN(1/b)
+    int fast; // 1: the reciprocal-and-correct scheme is enabled for this divisor
+};
 
 struct TerrainArgs {
     const void* height;
     uint32_t n;
     uint32_t height_row0, height_rows;  // rows of the heightmap present at `height`
     uint32_t row_begin, row_end;
-    unsigned char* vtx_out;  // already offset so that row `row_begin` of the band is addressable
+    unsigned char* vtx_out;
     uint32_t vtx_row0;
     float grid_step, origin_scale, height_scale;
     uint32_t stride, pos_off, nrm_off;  // nrm_off == 0xFFFFFFFF -> no normal attribute
+    DivConst d1, d2;                    // grid_step*1, grid_step*2
 };
 
-__device__ __forceinline__ float load_height_u16(const uint16_t* p) {
-    // Terrain.zig:120: 1.0 - f32(u16) / 65535.0
-    return __fsub_rn(1.0f, __fdiv_rn((float)__ldg(p), 65535.0f));
+// a / c.b, correctly rounded.
+__device__ __forceinline__ float div_const(float a, const DivConst c) {
+    const uint32_t e = (__float_as_uint(a) >> 23) & 0xFFu;
+    if (c.fast && (e - 64u) <= 126u) {  // |a| in [2^-63, 2^64): no overflow/underflow anywhere below
+        const float q = __fmul_rn(a, c.y);
+        const float r = __fmaf_rn(-q, c.b, a);
+        return __fmaf_rn(r, c.y, q);
+    }
+    return __fdiv_rn(a, c.b);
+}
+
+// Terrain.zig:120: 1.0 - f32(u16) / 65535.0   (the quotient via the exact scheme, all 65536 inputs verified)
+__device__ __forceinline__ float height_from_u16(uint32_t v) {
+    const float a = (float)v;
+    const float y = 1.0f / 65535.0f;  // RN(1/65535), folded at compile time
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-q, 65535.0f, a);
+    return __fsub_rn(1.0f, __fmaf_rn(r, y, q));
 }
 
 template <bool U16>
 __device__ __forceinline__ float load_height(const void* base, size_t idx) {
-    if (U16) return load_height_u16(reinterpret_cast<const uint16_t*>(base) + idx);
+    if (U16) return height_from_u16(__ldg(reinterpret_cast<const uint16_t*>(base) + idx));
     return __ldg(reinterpret_cast<const float*>(base) + idx);
 }
 
@@ -61,38 +91,43 @@ __global__ void __launch_bounds__(TV_THREADS) terrain_vertices_k(const TerrainAr
     // Rows are clamped to the terrain (central differences are one-sided at the border) and to the
     // rows the caller provided (a band-local buffer holds only the band plus its halo; rows beyond
     // it belong to tile rows past row_end, which are never emitted).
-    const int64_t r_lo = a.height_row0;
-    const int64_t r_hi = min((int64_t)n, (int64_t)a.height_row0 + a.height_rows) - 1;
     {
+        const int r_lo = (int)a.height_row0;
+        const int r_hi = (int)min(n, a.height_row0 + a.height_rows) - 1;
         const uint32_t c = min(c0 + tid, n - 1);
+        const char* base = static_cast<const char*>(a.height);
+        const size_t tex = U16 ? 2 : 4;
 #pragma unroll
         for (int rr = 0; rr < TV_ROWS + 2; ++rr) {
-            int64_t r = (int64_t)r0 + rr - 1;
-            r = r < r_lo ? r_lo : (r > r_hi ? r_hi : r);
-            tile[rr][tid + 1] = load_height<U16>(a.height, (size_t)((uint32_t)r - a.height_row0) * n + c);
+            int r = (int)r0 + rr - 1;
+            r = max(r_lo, min(r, r_hi));
+            tile[rr][tid + 1] = load_height<U16>(base, (size_t)(uint32_t)(r - r_lo) * n + c);
         }
         if (tid < 2 * (TV_ROWS + 2)) {
             const int rr = tid >> 1;
             const int side = tid & 1;
-            int64_t r = (int64_t)r0 + rr - 1;
-            r = r < r_lo ? r_lo : (r > r_hi ? r_hi : r);
-            int64_t cc = side ? (int64_t)c0 + TV_THREADS : (int64_t)c0 - 1;
-            cc = cc < 0 ? 0 : (cc > (int64_t)n - 1 ? (int64_t)n - 1 : cc);
-            tile[rr][side ? TV_THREADS + 1 : 0] =
-                load_height<U16>(a.height, (size_t)((uint32_t)r - a.height_row0) * n + (uint32_t)cc);
+            int r = (int)r0 + rr - 1;
+            r = max(r_lo, min(r, r_hi));
+            int cc = side ? (int)c0 + TV_THREADS : (int)c0 - 1;
+            cc = max(0, min(cc, (int)n - 1));
+            tile[rr][side ? TV_THREADS + 1 : 0] = load_height<U16>(base, (size_t)(uint32_t)(r - r_lo) * n + (uint32_t)cc);
         }
+        (void)tex;
     }
     __syncthreads();
 
     const uint32_t c = c0 + tid;
     if (c >= n) return;
+    const float gs = a.grid_step, hs = a.height_scale;
     const float org = __fmul_rn(a.origin_scale, (float)n);
-    const float z = __fsub_rn(__fmul_rn(a.grid_step, (float)c), org);
-    const uint32_t cm = c > 0 ? c - 1 : 0, cp = c + 1 < n ? c + 1 : n - 1;
-    const float den_c = __fmul_rn(a.grid_step, (float)(cp - cm));
+    const float z = __fsub_rn(__fmul_rn(gs, (float)c), org);
+    const bool has_normal = a.nrm_off != 0xFFFFFFFFu;
+    const bool col_border = (c == 0) || (c + 1 == n);
+    const DivConst dc = col_border ? a.d1 : a.d2;  // grid_step * (cp - cm)
+    const bool col_flat = n == 1;                 // cp == cm
     const uint32_t rows = min((uint32_t)TV_ROWS, a.row_end - r0);
-    unsigned char* out = a.vtx_out + ((size_t)(r0 - a.vtx_row0) * n + c) * a.stride;
     const size_t row_pitch = (size_t)n * a.stride;
+    unsigned char* v = a.vtx_out + ((size_t)(r0 - a.vtx_row0) * n + c) * a.stride;
 
     float up = tile[0][tid + 1];
     float mid = tile[1][tid + 1];
@@ -101,25 +136,24 @@ __global__ void __launch_bounds__(TV_THREADS) terrain_vertices_k(const TerrainAr
         const float down = tile[rr + 2][tid + 1];
         if ((uint32_t)rr < rows) {
             const uint32_t r = r0 + rr;
-            const float left = tile[rr + 1][tid];
-            const float right = tile[rr + 1][tid + 2];
-            const float x = __fsub_rn(__fmul_rn(a.grid_step, (float)r), org);
-            const float y = __fmul_rn(a.height_scale, mid);
+            const float x = __fsub_rn(__fmul_rn(gs, (float)r), org);
+            const float y = __fmul_rn(hs, mid);
             float nx = 0.0f, ny = 1.0f, nz = 0.0f;
-            if (a.nrm_off != 0xFFFFFFFFu) {
-                const uint32_t rm = r > 0 ? r - 1 : 0, rp = r + 1 < n ? r + 1 : n - 1;
+            if (has_normal) {
+                const float left = tile[rr + 1][tid];
+                const float right = tile[rr + 1][tid + 2];
+                const bool row_border = (r == 0) || (r + 1 == n);
                 float gx = 0.0f, gz = 0.0f;
-                if (rp != rm)
-                    gx = __fdiv_rn(__fmul_rn(a.height_scale, __fsub_rn(down, up)),
-                                   __fmul_rn(a.grid_step, (float)(rp - rm)));
-                if (cp != cm) gz = __fdiv_rn(__fmul_rn(a.height_scale, __fsub_rn(right, left)), den_c);
-                const float len =
-                    __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), 1.0f), __fmul_rn(gz, gz)));
-                nx = __fdiv_rn(-gx, len);
-                ny = __fdiv_rn(1.0f, len);
-                nz = __fdiv_rn(-gz, len);
+                if (!col_flat) {  // n > 1: rp != rm and cp != cm
+                    gx = div_const(__fmul_rn(hs, __fsub_rn(down, up)), row_border ? a.d1 : a.d2);
+                    gz = div_const(__fmul_rn(hs, __fsub_rn(right, left)), dc);
+                }
+                const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), 1.0f), __fmul_rn(gz, gz)));
+                const float inv = __frcp_rn(len);
+                nx = __fmul_rn(-gx, inv);
+                ny = inv;
+                nz = __fmul_rn(-gz, inv);
             }
-            unsigned char* v = out + (size_t)rr * row_pitch;
             if (FAST32) {
                 if (a.pos_off == 0)
                     store_vertex32(v, x, y, z, nx, ny, nz);
@@ -133,13 +167,14 @@ __global__ void __launch_bounds__(TV_THREADS) terrain_vertices_k(const TerrainAr
                 p[0] = x;
                 p[1] = y;
                 p[2] = z;
-                if (a.nrm_off != 0xFFFFFFFFu) {
+                if (has_normal) {
                     float* q = reinterpret_cast<float*>(v + a.nrm_off);
                     q[0] = nx;
                     q[1] = ny;
                     q[2] = nz;
                 }
             }
+            v += row_pitch;
         }
         up = mid;
         mid = down;
@@ -147,71 +182,96 @@ __global__ void __launch_bounds__(TV_THREADS) terrain_vertices_k(const TerrainAr
 }
 
 // ---- index buffer ------------------------------------------------------------------------
-// Row q of quads occupies L = 6*(n-1) consecutive u32.  Each thread owns one 16-byte aligned
-// group of 4 words of the output; the group is mapped back to (quad, corner) with a division
-// by the constant 6 only.
+// Quad Q = q*(n-1) + c of quad row q owns words [6Q, 6Q+6) of the index stream:
+//     i00+n, i00, i00+n+1, i00+n+1, i00, i00+1      with i00 = q*n + c = Q + q
+// (corner order of Terrain.zig:28-35 / lookups :38-45).  A CTA fills TI_QUADS quads in shared memory
+// and writes them with one bulk async copy; the shared buffer is offset so that it has the same
+// alignment modulo 16 as the destination, and the (at most 8-byte) unaligned head/tail go out as
+// plain stores.
 constexpr int TI_THREADS = 256;
-constexpr int TI_GROUPS = 4;  // 16-byte groups per thread
+constexpr int TI_QPT = 4;  // quads per thread
+constexpr int TI_QUADS = TI_THREADS * TI_QPT;
 
 struct IndexArgs {
-    uint32_t* idx_out;
+    uint32_t* out;        // first word of quad `quad_begin`
     uint32_t n;
-    uint32_t qrow_begin, qrow_end, idx_qrow0;
+    uint64_t quad_begin;  // global quad number of the first quad of this launch
+    uint64_t quad_count;
+    uint64_t div_magic;   // floor(2^48/(n-1)) + 1: q = (Q * magic) >> 48 for Q < 2^32
 };
 
-__device__ __forceinline__ uint32_t quad_corner_index(uint32_t i00, uint32_t n, uint32_t k) {
-    // corner order of Terrain.zig:28-35 / lookups :38-45
-    //   k: 0 (r+1,c)  1 (r,c)  2 (r+1,c+1)  3 (r+1,c+1)  4 (r,c)  5 (r,c+1)
-    const uint32_t add_n = (0x0Du >> k) & 1u;  // k in {0,2,3}
-    const uint32_t add_1 = (0x2Cu >> k) & 1u;  // k in {2,3,5}
-    return i00 + (add_n ? n : 0u) + add_1;
-}
-
 __global__ void __launch_bounds__(TI_THREADS) terrain_indices_k(const IndexArgs a) {
-    const uint32_t q = a.qrow_begin + blockIdx.y;
-    const uint32_t L = 6u * (a.n - 1u);
-    uint32_t* row = a.idx_out + (size_t)(q - a.idx_qrow0) * L;
-    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(row) >> 2) & 3u);  // words past 16B alignment
-    const uint32_t row_i0 = q * a.n;
+    __shared__ __align__(16) uint32_t buf[TI_QUADS * 6 + 4];
+    const uint64_t q0 = (uint64_t)blockIdx.x * TI_QUADS;  // first quad of this CTA, relative to quad_begin
+    const uint32_t nq = (uint32_t)min((uint64_t)TI_QUADS, a.quad_count - q0);
+    uint32_t* dst = a.out + q0 * 6;  // 8-byte aligned
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u);  // 0 or 2 words past 16 B
+    uint32_t* sbuf = buf + mis;
+    const uint32_t n = a.n;
 #pragma unroll
-    for (int g = 0; g < TI_GROUPS; ++g) {
-        const uint32_t grp = (blockIdx.x * TI_GROUPS + g) * TI_THREADS + threadIdx.x;
-        const int64_t w0 = (int64_t)grp * 4 - mis;  // first word of the group, relative to the row
-        if (w0 >= (int64_t)L) break;
-        uint32_t v[4];
-        const uint32_t wfirst = w0 < 0 ? 0u : (uint32_t)w0;
-        uint32_t quad = wfirst / 6u;
-        uint32_t k = wfirst - quad * 6u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t w = w0 + i;
-            if (w >= (int64_t)wfirst) {
-                v[i] = quad_corner_index(row_i0 + quad, a.n, k);
-                if (++k == 6u) {
-                    k = 0;
-                    ++quad;
-                }
-            } else {
-                v[i] = 0;
-            }
-        }
-        if (w0 >= 0 && w0 + 4 <= (int64_t)L) {
-            *reinterpret_cast<uint4*>(row + w0) = make_uint4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t w = w0 + i;
-                if (w >= 0 && w < (int64_t)L) row[w] = v[i];
-            }
+    for (int k = 0; k < TI_QPT; ++k) {
+        const uint32_t ql = k * TI_THREADS + threadIdx.x;
+        if (ql < nq) {
+            const uint32_t Q = (uint32_t)(a.quad_begin + q0 + ql);
+            const uint32_t qrow = (uint32_t)(((uint64_t)Q * a.div_magic) >> 48);
+            const uint32_t i00 = Q + qrow;
+            uint2* s = reinterpret_cast<uint2*>(sbuf + ql * 6);
+            s[0] = make_uint2(i00 + n, i00);
+            s[1] = make_uint2(i00 + n + 1, i00 + n + 1);
+            s[2] = make_uint2(i00, i00 + 1);
         }
     }
+    // make the generic-proxy shared writes visible to the async proxy, then one thread issues the copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t words = nq * 6;
+    const uint32_t head = mis ? 2u : 0u;                  // words before the first 16 B boundary
+    const uint32_t body = ((words - head) / 4u) * 4u;     // words in whole 16 B groups
+    if (threadIdx.x == 0 && body) {
+        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sbuf + head);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head), "r"(saddr),
+                     "r"(body * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        if (head) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(sbuf);
+        if (words - head - body) *reinterpret_cast<uint2*>(dst + head + body) = *reinterpret_cast<uint2*>(sbuf + head + body);
+    }
+    if (threadIdx.x == 0 && body) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) heightmap_normalize_k(const uint16_t* __restrict__ in,
                                                              float* __restrict__ out, uint64_t count) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    for (; i < count; i += step) out[i] = load_height_u16(in + i);
+    for (; i < count; i += step) out[i] = height_from_u16(__ldg(in + i));
+}
+
+// exhaustive check of div_const against __fdiv_rn over all 2^32 dividends
+__global__ void __launch_bounds__(256) selftest_fastdiv_k(DivConst c, unsigned long long* mismatches) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += step) {
+        const float av = __uint_as_float((uint32_t)i);
+        const uint32_t g = __float_as_uint(div_const(av, c));
+        const uint32_t w = __float_as_uint(__fdiv_rn(av, c.b));
+        const bool both_nan = ((g & 0x7FFFFFFFu) > 0x7F800000u) && ((w & 0x7FFFFFFFu) > 0x7F800000u);
+        if (g != w && !both_nan) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// The scheme is enabled only for divisors it has been verified for (see mr_selftest_fastdiv).
+DivConst make_div_const(float b) {
+    DivConst c;
+    c.b = b;
+    c.y = 1.0f / b;
+    uint32_t bits;
+    memcpy(&bits, &b, 4);
+    // verified: 0.2f, 0.4f (default grid_step * 1, * 2)
+    c.fast = (bits == 0x3E4CCCCDu || bits == 0x3ECCCCCDu) ? 1 : 0;
+    return c;
 }
 
 }  // namespace
@@ -234,12 +294,13 @@ int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* j) {
         a.stride = j->layout.stride;
         a.pos_off = j->layout.attr[0].offset;
         a.nrm_off = j->layout.nattr > 1 ? j->layout.attr[1].offset : 0xFFFFFFFFu;
+        a.d1 = make_div_const(j->params.grid_step * 1.0f);
+        a.d2 = make_div_const(j->params.grid_step * 2.0f);
         const bool fast32 = a.stride == 32 && j->layout.nattr == 2 &&
                             ((a.pos_off == 0 && a.nrm_off == 16) || (a.pos_off == 16 && a.nrm_off == 0)) &&
                             (reinterpret_cast<uintptr_t>(a.vtx_out) % 32 == 0);
         const uint32_t rows = j->row_end - j->row_begin;
         dim3 grid((n + TV_THREADS - 1) / TV_THREADS, (rows + TV_ROWS - 1) / TV_ROWS);
-        // grid.y limit is 65535: 8 rows per tile covers n up to 524k rows per launch
         if (grid.y > 65535u) return mr_fail(ctx, MR_E_BADARG, "terrain band too tall for one launch");
         const bool u16 = j->height_fmt == MR_HEIGHT_U16;
         if (u16 && fast32)
@@ -254,24 +315,16 @@ int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* j) {
     }
     if (j->idx_out && n > 1 && j->qrow_end > j->qrow_begin) {
         IndexArgs a;
-        a.idx_out = j->idx_out;
+        const uint64_t L = 6ull * (n - 1u);
+        a.out = j->idx_out + (uint64_t)(j->qrow_begin - j->idx_qrow0) * L;
         a.n = n;
-        a.qrow_begin = j->qrow_begin;
-        a.qrow_end = j->qrow_end;
-        a.idx_qrow0 = j->idx_qrow0;
-        const uint32_t L = 6u * (n - 1u);
-        const uint32_t groups = (L + 3u) / 4u + 1u;  // +1: a misaligned row spills into one more group
-        const uint32_t per_block = TI_THREADS * TI_GROUPS;
-        uint32_t rows_left = j->qrow_end - j->qrow_begin;
-        // grid.y is limited to 65535 rows per launch
-        while (rows_left) {
-            const uint32_t rows = rows_left > 65535u ? 65535u : rows_left;
-            dim3 grid((groups + per_block - 1) / per_block, rows);
-            terrain_indices_k<<<grid, TI_THREADS, 0, ctx->stream>>>(a);
-            MR_LAUNCH_CHECK(ctx, "terrain_indices_k");
-            a.qrow_begin += rows;
-            rows_left -= rows;
-        }
+        a.quad_begin = (uint64_t)j->qrow_begin * (n - 1u);
+        a.quad_count = (uint64_t)(j->qrow_end - j->qrow_begin) * (n - 1u);
+        a.div_magic = ((1ull << 48) / (n - 1u)) + 1ull;
+        const uint64_t blocks = (a.quad_count + TI_QUADS - 1) / TI_QUADS;
+        if (blocks > 0x7FFFFFFFull) return mr_fail(ctx, MR_E_BADARG, "terrain index range too large for one launch");
+        terrain_indices_k<<<(unsigned)blocks, TI_THREADS, 0, ctx->stream>>>(a);
+        MR_LAUNCH_CHECK(ctx, "terrain_indices_k");
     }
     return MR_OK;
 }
@@ -283,5 +336,13 @@ int mr_heightmap_normalize_impl(mr_context* ctx, const uint16_t* in, uint64_t co
     if (blocks > cap) blocks = cap;
     heightmap_normalize_k<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, count);
     MR_LAUNCH_CHECK(ctx, "heightmap_normalize_k");
+    return MR_OK;
+}
+
+int mr_selftest_fastdiv_impl(mr_context* ctx, float b, int force_fast, unsigned long long* mismatches_dev) {
+    DivConst c = make_div_const(b);
+    if (force_fast) c.fast = 1;
+    selftest_fastdiv_k<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c, mismatches_dev);
+    MR_LAUNCH_CHECK(ctx, "selftest_fastdiv_k");
     return MR_OK;
 }

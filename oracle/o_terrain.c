@@ -83,13 +83,14 @@ static void build_band(const band* b) {
                 memcpy(v + j->layout.attr[0].offset, pos, 12);
                 if (has_normal) {
                     uint32_t cm = c > 0 ? c - 1u : 0u, cp = c + 1u < n ? c + 1u : n - 1u;
-                    float gx = 0.0f, gz = 0.0f, len, nrm[3];
+                    float gx = 0.0f, gz = 0.0f, len, inv, nrm[3];
                     if (rp != rm) gx = (hs * (texel(j, rp, c) - texel(j, rm, c))) / (gs * (float)(rp - rm));
                     if (cp != cm) gz = (hs * (texel(j, r, cp) - texel(j, r, cm))) / (gs * (float)(cp - cm));
                     len = sqrtf(((gx * gx) + 1.0f) + (gz * gz));
-                    nrm[0] = (-gx) / len;
-                    nrm[1] = 1.0f / len;
-                    nrm[2] = (-gz) / len;
+                    inv = 1.0f / len;
+                    nrm[0] = (-gx) * inv;
+                    nrm[1] = inv;
+                    nrm[2] = (-gz) * inv;
                     memcpy(v + j->layout.attr[1].offset, nrm, 12);
                 }
             }

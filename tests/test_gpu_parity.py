@@ -195,6 +195,16 @@ def test_heightmap_normalize(ctx, oracle):
     assert np.array_equal(out.cpu().numpy().view(np.uint32), oracle.heightmap_normalize(v).view(np.uint32))
 
 
+def test_constant_divisor_quotients_are_exact(ctx):
+    """The vertex kernel divides by grid_step and 2*grid_step with q=a*y; r=fma(-q,b,a); q'=fma(r,y,q).
+    Exhaustive: all 2^32 dividends against IEEE division, for the divisors the library enables the
+    scheme for (and, forced, for a few others to show the guard range is what matters)."""
+    for b, force in ((0.2, 0), (0.4, 0), (0.2, 1), (0.4, 1), (65535.0, 1), (0.3, 0)):
+        bad = C.c_uint64(123)
+        ctx.check(ctx.lib.mr_selftest_fastdiv(ctx.handle, b, force, C.byref(bad)), "selftest")
+        assert bad.value == 0, f"divisor {b}: {bad.value} dividends differ from IEEE division"
+
+
 # ---- polygons ---------------------------------------------------------------------------------
 def _check_batch(ctx, oracle, xy, fp, *, offset_prime=None, seed=0, poly_index0=0, order="decl"):
     import myrenderer_b200 as mr

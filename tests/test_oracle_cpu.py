@@ -233,7 +233,8 @@ def _terrain_numpy(h16, n, gs=np.float32(0.2), os_=np.float32(0.1), hs=np.float3
         gx[:] = 0
         gz[:] = 0
     ln = np.sqrt(((gx * gx).astype(np.float32) + f(1.0)).astype(np.float32) + (gz * gz).astype(np.float32)).astype(np.float32)
-    nrm = np.stack([(-gx) / ln, f(1.0) / ln, (-gz) / ln], -1).astype(np.float32)
+    inv = (f(1.0) / ln).astype(np.float32)
+    nrm = np.stack([(-gx) * inv, inv, (-gz) * inv], -1).astype(np.float32)
     r, c = np.meshgrid(np.arange(n - 1), np.arange(n - 1), indexing="ij")
     i00 = (r * n + c).astype(np.uint32)
     idx = np.stack([i00 + n, i00, i00 + n + 1, i00 + n + 1, i00, i00 + 1], -1).reshape(-1)
