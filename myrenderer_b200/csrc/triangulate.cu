@@ -18,6 +18,7 @@
 // checked per triangle with a musl-exact atan2f; if any check fails the polygon falls back to a
 // literal restatement of the loop.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "unirand.cuh"
 
@@ -103,12 +104,15 @@ struct BatchArgs {
     uint32_t* ntri_out;
     uint32_t stride, off_x, off_c;  // off_c == 0xFFFFFFFF: no colour attribute
     int fast32;                     // stride 32, offsets {0,16} in either order, 32B-aligned base
+    uint32_t tune;                  // experiment knobs (MR_TUNE), see triangulate_fast.cuh
     // work lists
-    const uint32_t* order;     // polygon ids grouped by class
+    const uint32_t* order;        // polygon ids grouped by class
     const uint32_t* class_begin;  // NUM_CLASSES+1
-    uint32_t* queue_head;      // NUM_CLASSES + 2 (last two: tier-1 queues)
-    uint32_t* overflow_list;   // npoly
-    uint32_t* overflow_count;
+    uint32_t* queue_head;         // [0,8): fast tier per class; [8,16): spec tier per class; [16,18): general
+    uint32_t* spec_list;          // npoly, class c's overflow at class_begin[c]..
+    uint32_t* spec_count;         // NUM_CLASSES
+    uint32_t* general_list;       // npoly
+    uint32_t* general_count;
     unsigned char* tier1_ws;
     size_t tier1_ws_stride;
 };
@@ -1021,49 +1025,60 @@ __device__ __forceinline__ void write_result(const BatchArgs& a, uint32_t pi, co
     }
 }
 
+#include "triangulate_fast.cuh"
+
 // ---- kernels ----------------------------------------------------------------------------------
-// tier 0: class c, shared-memory workspace
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_tier0_k(const BatchArgs a, int c) {
+// Fast path, class c, shared-memory workspace.  spec == 0: the class's polygons with arenas sized for
+// the typical case; spec == 1: the polygons that outgrew those, with arenas at the contract caps.
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 6) triangulate_fast_k(const BatchArgs a, int c, int spec) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const Caps caps = tier0_caps(c);
-    const WsLayout L = ws_layout(caps, true);
+    const FCaps caps = fast_caps(c, spec != 0);
+    const FLayout L = fast_layout(caps);
     unsigned char* ws = smem + (size_t)(threadIdx.x >> 5) * L.total;  // blockDim.x/32 warps per block
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t begin = a.class_begin[c], end = a.class_begin[c + 1];
+    const uint32_t begin = a.class_begin[c];
+    const uint32_t count = spec ? a.spec_count[c] : (a.class_begin[c + 1] - begin);
+    const uint32_t* list = spec ? a.spec_list : a.order;
+    uint32_t* head = spec ? &a.queue_head[NUM_CLASSES + c] : &a.queue_head[c];
     for (;;) {
         uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(&a.queue_head[c], 1u);
-        idx = __shfl_sync(0xFFFFFFFFu, idx, 0) + begin;
-        if (idx >= end) break;
-        const uint32_t pi = a.order[idx];
+        if (lane == 0) idx = atomicAdd(head, 1u);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= count) break;
+        const uint32_t pi = list[begin + idx];
         Result r;
-        process_polygon(a, pi, ws, caps, L, false, &r);
-        if (r.requeue) {
-            if (lane == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = pi;
-        } else {
+        int rc = process_polygon_fast(a, pi, ws, caps, L, &r);
+        if (rc == F_REQUEUE_SPEC && spec) rc = F_REQUEUE_GENERAL;  // the spec tier has no bigger shared-memory tier
+        if (rc == F_DONE) {
             write_result(a, pi, r);
+        } else if (lane == 0) {
+            if (rc == F_REQUEUE_SPEC)
+                a.spec_list[begin + atomicAdd(&a.spec_count[c], 1u)] = pi;
+            else
+                a.general_list[atomicAdd(a.general_count, 1u)] = pi;
         }
         __syncwarp();
     }
 }
 
-// tier 1: class 7 polygons and everything re-queued from tier 0; global-memory workspace
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_tier1_k(const BatchArgs a, uint32_t nmax, int which) {
+// General path (float compares, 12-byte nodes, literal fallback loop), global-memory workspace:
+// which == 0: polygons handed over by the fast path (coincident points, not-acute corner, oversized
+// mountain lists; n <= 1024); which == 1: class 7 (1024 < n <= MR_MAX_POLYGON_POINTS).
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_general_k(const BatchArgs a, uint32_t nmax, int which) {
     const Caps caps = tier1_caps(nmax);
     const WsLayout L = ws_layout(caps, false);
     const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char* ws = a.tier1_ws + (size_t)warp_global * a.tier1_ws_stride;
     const uint32_t lane = threadIdx.x & 31u;
-    // which == 0: polygons re-queued from tier 0 (n <= 1024); which == 1: class 7 (n up to MR_MAX)
     const uint32_t c = NUM_CLASSES - 1;
     const uint32_t begin = a.class_begin[c], end = a.class_begin[c + 1];
-    const uint32_t total = which == 0 ? *a.overflow_count : (end - begin);
+    const uint32_t total = which == 0 ? *a.general_count : (end - begin);
     for (;;) {
         uint32_t idx = 0;
-        if (lane == 0) idx = atomicAdd(&a.queue_head[NUM_CLASSES + which], 1u);
+        if (lane == 0) idx = atomicAdd(&a.queue_head[2 * NUM_CLASSES + which], 1u);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= total) break;
-        const uint32_t pi = which == 0 ? a.overflow_list[idx] : a.order[begin + idx];
+        const uint32_t pi = which == 0 ? a.general_list[idx] : a.order[begin + idx];
         Result r;
         process_polygon(a, pi, ws, caps, L, true, &r);
         write_result(a, pi, r);
@@ -1206,19 +1221,21 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     const uint32_t npoly = j->npoly;
     if (npoly == 0) return MR_OK;
 
-    // work-list memory: class_count[8] class_begin[9] cursor[8] queue_head[9] overflow_count[1] order[npoly] overflow[npoly]
+    // work-list memory: a 64-word header followed by order[npoly], spec_list[npoly], general_list[npoly]
     const size_t header_words = 64;
     void* work = nullptr;
-    int rc = mr_scratch(ctx, SLOT_WORK, (header_words + 2 * (size_t)npoly) * 4, &work);
+    int rc = mr_scratch(ctx, SLOT_WORK, (header_words + 3 * (size_t)npoly) * 4, &work);
     if (rc) return rc;
     uint32_t* w = static_cast<uint32_t*>(work);
-    uint32_t* class_count = w;
-    uint32_t* class_begin = w + 8;
-    uint32_t* cursor = w + 24;
-    uint32_t* queue_head = w + 32;
-    uint32_t* overflow_count = w + 48;
+    uint32_t* class_count = w;        // 8
+    uint32_t* class_begin = w + 8;    // 9
+    uint32_t* cursor = w + 18;        // 8
+    uint32_t* queue_head = w + 26;    // 18
+    uint32_t* spec_count = w + 44;    // 8
+    uint32_t* general_count = w + 52; // 1
     uint32_t* order = w + header_words;
-    uint32_t* overflow_list = order + npoly;
+    uint32_t* spec_list = order + npoly;
+    uint32_t* general_list = spec_list + npoly;
     MR_CUDA(ctx, cudaMemsetAsync(w, 0, header_words * 4, ctx->stream));
 
     const unsigned cblocks = (unsigned)std::min<uint64_t>(((uint64_t)npoly + 255) / 256, (uint64_t)ctx->sm_count * 4);
@@ -1251,28 +1268,39 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                 reinterpret_cast<uintptr_t>(a.vtx_out) % 32 == 0)
                    ? 1
                    : 0;
+    {
+        const char* t = getenv("MR_TUNE");
+        a.tune = t ? (uint32_t)strtoul(t, nullptr, 0) : 0u;
+    }
     a.order = order;
     a.class_begin = class_begin;
     a.queue_head = queue_head;
-    a.overflow_list = overflow_list;
-    a.overflow_count = overflow_count;
+    a.spec_list = spec_list;
+    a.spec_count = spec_count;
+    a.general_list = general_list;
+    a.general_count = general_count;
+    a.tier1_ws = nullptr;
+    a.tier1_ws_stride = 0;
 
-    for (int c = 0; c < NUM_CLASSES - 1; ++c) {
-        const Caps caps = tier0_caps(c);
-        const WsLayout L = ws_layout(caps, true);
-        int wpb = MAX_WARPS_PER_BLOCK;
-        while (wpb > 1 && L.total * wpb > ctx->smem_optin / 2) wpb >>= 1;  // keep >= 2 blocks per SM when possible
-        const size_t smem = L.total * wpb;
-        if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "tier-0 workspace exceeds shared memory");
-        MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_tier0_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_tier0_k, wpb * 32, smem));
-        if (per_sm < 1) per_sm = 1;
-        const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
-        triangulate_tier0_k<<<grid, wpb * 32, smem, ctx->stream>>>(a, c);
-        MR_LAUNCH_CHECK(ctx, "triangulate_tier0_k");
+    // fast path: per class, first with typical-case arenas, then the overflow with contract-cap arenas
+    for (int spec = 0; spec < 2; ++spec) {
+        for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+            const FCaps caps = fast_caps(c, spec != 0);
+            const FLayout L = fast_layout(caps);
+            int wpb = MAX_WARPS_PER_BLOCK;
+            while (wpb > 1 && L.total * wpb > ctx->smem_optin / 2) wpb >>= 1;  // keep >= 2 blocks per SM when possible
+            const size_t smem = L.total * wpb;
+            if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
+            MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_fast_k, wpb * 32, smem));
+            if (per_sm < 1) per_sm = 1;
+            const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
+            triangulate_fast_k<<<grid, wpb * 32, smem, ctx->stream>>>(a, c, spec);
+            MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");
+        }
     }
-    // tier 1: global-memory workspaces, one per warp of the grid
+    // general path: global-memory workspaces, one per warp of the grid
     for (int which = 0; which < 2; ++which) {
         const uint32_t nmax = which == 0 ? class_nmax(NUM_CLASSES - 2) : MR_MAX_POLYGON_POINTS;
         const Caps c1 = tier1_caps(nmax);
@@ -1284,8 +1312,8 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
         if (rc) return rc;
         a.tier1_ws = static_cast<unsigned char*>(t1);
         a.tier1_ws_stride = L1.total;
-        triangulate_tier1_k<<<blocks, wpb * 32, 0, ctx->stream>>>(a, nmax, which);
-        MR_LAUNCH_CHECK(ctx, "triangulate_tier1_k");
+        triangulate_general_k<<<blocks, wpb * 32, 0, ctx->stream>>>(a, nmax, which);
+        MR_LAUNCH_CHECK(ctx, "triangulate_general_k");
     }
     return MR_OK;
 }

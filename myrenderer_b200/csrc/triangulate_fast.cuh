@@ -1,0 +1,842 @@
+// triangulate_fast.cuh -- the fast path of the Seidel kernel (included inside triangulate.cu's
+// anonymous namespace).  Same algorithm, same emit sequence as the general path; it applies when
+// no two points of the polygon have identical coordinates (checked per polygon), which allows:
+//
+//   * rank space.  Points are renamed by their position in the (y, x) order, so
+//     point_is_above(a, b) (Triangulation.zig:128-136) is the integer compare a < b on values that
+//     are already in registers; coordinates are only loaded for is_left_of.  Original ids come
+//     back at emission (the emit order of :405-422 is defined on original ids).
+//   * 8-byte nodes: {child1:16 | child2:16, pa:14 | type:2 | pb:16} fetched with one LDS.64;
+//     the crumb of segment nodes lives in a side array (read only by the mountain scan); the
+//     breadcrumb chain of the segment search (:253-257,:306-310) is an explicit stack -- the
+//     reference restores every crumb to null before the search returns, so this is unobservable.
+//   * no null checks on inner nodes: point and segment nodes always have both children and their
+//     points set (they are written non-null at :183-192 and :347-360); the unwraps that CAN fail
+//     (:330 trapezoid.point2, :524-527, :58) are kept.
+//   * lane-parallel point location.  Inner nodes never change once written (only trapezoid leaves
+//     are converted in place), so a node that was on a point's search path stays on it.  loc[p]
+//     caches the deepest node reached so far for every not-yet-inserted point; all lanes advance
+//     the caches between insertions and add_point continues from the cache instead of the root.
+//     Result: identical descents, but the bulk of them run 32 wide.
+//   * lane-parallel segment search (items tier).  The search of add_segment (:231-314) is a
+//     pre-order walk whose decisions depend only on immutable inner nodes, so for every edge that
+//     has not been inserted yet the walk can be kept *in progress*: an ordered linked list of
+//     "items", each the deepest node reached on one branch.  When a leaf is converted by a later
+//     insertion, the item simply continues from it (a straddled point node appends a sibling item
+//     right after, which is exactly the order in which the reference would push the leaves).  All
+//     lanes advance all pending items between insertions; at its own insertion an edge only
+//     finishes the last step or two and copies its list into node_stack.  Duplicates (the same
+//     trapezoid reached over two paths, which the reference pushes twice) are kept as they are.
+//   * pass 2 picks the next trapezoid with a warp arg-min (REDUX) over the stack instead of the
+//     O(k) scan of :329-337: same winner, because ties go to the lowest stack index in both.
+#pragma once
+
+constexpr uint32_t FNIL14 = 0x3FFFu;  // null in the 14-bit pa field
+constexpr uint32_t FNIL = 0xFFFFu;
+
+struct FCaps {
+    uint32_t nmax, node_cap, stack_cap, add_cap;
+    uint32_t item_cap;  // 0: no conflict lists (the segment search runs from the root at insertion)
+};
+// tight: sized for the typical polygon of the class; spec: the contract caps (second chance in shared memory)
+__host__ __device__ inline FCaps fast_caps(int c, bool spec) {
+    FCaps k;
+    k.nmax = class_nmax(c);
+    if (!spec) {
+        k.node_cap = 6u * k.nmax + 16u;
+        k.stack_cap = k.nmax + 32u;
+        k.add_cap = 2u * k.nmax + 16u;
+        // conflict lists pay for themselves on larger polygons only (measured: 1.35-1.55x for n up to 1024,
+        // a small loss for n <= 64 where the per-edge polling overhead exceeds the search it saves)
+        k.item_cap = c >= 3 ? 6u * k.nmax + 64u : 0u;  // 6 B per item >= the 16 B per add that reuse the pool later
+    } else {
+        k.item_cap = 0;
+        k.node_cap = MR_NODE_CAP(k.nmax);
+        k.stack_cap = MR_STACK_CAP(k.nmax);
+        k.add_cap = 4u * k.nmax + 32u;  // sort arrays (20 B per add) alias the node arena (10 B per node)
+    }
+    return k;
+}
+
+struct FLayout {
+    size_t sxy, orig, rk, loc, cstack, stack, nodes, crumb, add_pp, add_key, add_m, mcount, mstart, efirst, total;
+    size_t it_node, it_next, it_edge, ehead, eul, ctr;  // items tier only
+};
+__host__ __device__ inline FLayout fast_layout(const FCaps& k) {
+    FLayout L;
+    size_t o = 0;
+    L.sxy = o;     o += align16((size_t)k.nmax * 8);
+    L.orig = o;    o += align16((size_t)k.nmax * 2);
+    L.rk = o;      o += align16((size_t)k.nmax * 2);
+    L.loc = o;     o += align16((size_t)k.nmax * 2);
+    L.cstack = o;  o += align16((size_t)k.nmax * 2);
+    L.stack = o;   o += align16((size_t)k.stack_cap * 2);
+    L.nodes = o;   o += align16((size_t)k.node_cap * 8);
+    L.crumb = o;   o += align16((size_t)k.node_cap * 2);
+    // mountain-phase arrays; in the items tier they reuse the item pool (dead once part 1 is done)
+    const size_t pool = o;
+    L.add_pp = o;  o += align16((size_t)k.add_cap * 4);
+    L.add_key = o; o += align16((size_t)k.add_cap * 4);
+    L.add_m = o;   o += align16((size_t)k.add_cap * 2);
+    L.mcount = o;  o += align16((size_t)k.add_cap * 4);
+    L.mstart = o;  o += align16((size_t)(k.add_cap + 1) * 2);
+    const size_t mountain_end = o;
+    L.it_node = L.it_next = L.it_edge = L.ehead = L.eul = L.ctr = 0;
+    if (k.item_cap) {
+        o = pool;
+        L.it_node = o; o += align16((size_t)k.item_cap * 2);
+        L.it_next = o; o += align16((size_t)k.item_cap * 2);
+        L.it_edge = o; o += align16((size_t)k.item_cap * 2);
+        if (o < mountain_end) o = mountain_end;
+        L.ehead = o;   o += align16((size_t)k.nmax * 2);
+        L.eul = o;     o += align16((size_t)k.nmax * 4);
+        L.ctr = o;     o += 16;
+    }
+    L.efirst = o;  o += align16((size_t)k.nmax * 2);
+    L.total = o;
+    return L;
+}
+
+// outcome of the fast path besides a Result
+enum : int { F_DONE = 0, F_REQUEUE_SPEC = 1, F_REQUEUE_GENERAL = 2 };
+
+struct FPoly {
+    const float2* sxy;
+    uint2* nd;
+    uint16_t* crumb;
+    uint16_t* stack;
+    uint16_t* cstack;
+    uint32_t nnodes, nstack, status;
+    uint32_t tier_node_cap, tier_stack_cap, spec_node_cap, spec_stack_cap;
+    bool requeue;
+
+    __device__ __forceinline__ uint32_t alloc() {
+        if (nnodes >= spec_node_cap) {
+            status |= MR_POLY_ARENA;
+            return FNIL;
+        }
+        if (nnodes >= tier_node_cap) {
+            requeue = true;
+            return FNIL;
+        }
+        return nnodes++;
+    }
+    // is_left_of(point P, segment a->b)  Triangulation.zig:117-126
+    __device__ __forceinline__ bool left_of(float2 P, uint32_t a, uint32_t b) const {
+        const float2 A = sxy[a], B = sxy[b];
+        const float mul1 = __fmul_rn(__fsub_rn(B.x, A.x), __fsub_rn(P.y, A.y));
+        const float mul2 = __fmul_rn(__fsub_rn(B.y, A.y), __fsub_rn(P.x, A.x));
+        return __fsub_rn(mul1, mul2) > 0.0f;
+    }
+    __device__ __forceinline__ static uint32_t type_of(uint32_t w1) { return (w1 >> 14) & 3u; }
+
+    // the descent of add_point (:144-167) from `base`; returns the trapezoid, or FNIL when the walk
+    // meets the point's own node (already inserted)
+    __device__ __forceinline__ uint32_t locate(uint32_t pid, float2 P, uint32_t base) const {
+        for (;;) {
+            const uint2 v = nd[base];
+            const uint32_t t = type_of(v.y);
+            if (t == T_TRAPEZOID) return base;
+            const uint32_t pa = v.y & FNIL14;
+            bool first;
+            if (t == T_POINT) {
+                if (pa == pid) return FNIL;
+                first = pid < pa;  // point_is_above(pid, pa) in rank space
+            } else {
+                first = left_of(P, pa, v.y >> 16);
+            }
+            base = first ? (v.x & 0xFFFFu) : (v.x >> 16);
+        }
+    }
+
+    // :169-192 split trapezoid `base` at point pid
+    __device__ __forceinline__ bool split(uint32_t base, uint32_t pid) {
+        const uint2 v = nd[base];
+        const uint32_t lower = alloc();  // :178 lower first
+        const uint32_t upper = alloc();  // :179
+        if (lower == FNIL || upper == FNIL) return false;
+        nd[lower] = make_uint2(v.x, (v.y & 0xFFFFC000u) | pid);        // point1 = pid
+        nd[upper] = make_uint2(v.x, (v.y & 0x0000FFFFu) | (pid << 16));  // point2 = pid
+        const uint16_t cb = crumb[base];
+        crumb[lower] = cb;
+        crumb[upper] = cb;
+        nd[base] = make_uint2(upper | (lower << 16), pid | (T_POINT << 14) | (FNIL << 16));
+        crumb[base] = (uint16_t)FNIL;
+        return true;
+    }
+
+    __device__ __forceinline__ bool push(uint32_t id) {
+        if (nstack >= spec_stack_cap) {
+            status |= MR_POLY_ARENA;
+            return false;
+        }
+        if (nstack >= tier_stack_cap) {
+            requeue = true;
+            return false;
+        }
+        stack[nstack++] = (uint16_t)id;
+        return true;
+    }
+
+    // One step of the segment search (:234-296) at inner node v for segment (up, lo): returns the child
+    // to continue with; *both is set when child2 has to be searched afterwards (breadcrumb case).
+    __device__ __forceinline__ uint32_t dfs_step(const uint2 v, uint32_t up, uint32_t lo, const float2 Pu,
+                                                  const float2 Pl, bool* both) const {
+        const uint32_t pa = v.y & FNIL14;
+        bool first;  // take child1
+        *both = false;
+        if (type_of(v.y) == T_POINT) {  // :234-259
+            if (up == pa) {
+                first = false;
+            } else if (lo == pa) {
+                first = true;
+            } else if (pa < up) {  // top_point_is_below
+                first = false;
+            } else if (lo < pa) {  // bottom_point_is_above
+                first = true;
+            } else {  // straddles: breadcrumb, then child1
+                *both = true;
+                first = true;
+            }
+        } else {  // :260-296
+            const uint32_t o1 = pa, o2 = v.y >> 16;
+            if (up == o2 || up == o1) {
+                first = left_of(Pl, o1, o2);
+            } else if (lo == o1 || lo == o2) {
+                first = left_of(Pu, o1, o2);
+            } else {
+                const bool top_is_above = up < o1;
+                const bool bottom_is_below = lo < o2;  // point_is_above(lower, other_p2), as written
+                if (top_is_above && bottom_is_below)
+                    first = !left_of(sxy[o1], up, lo);
+                else if (top_is_above)
+                    first = left_of(Pl, o1, o2);
+                else
+                    first = left_of(Pu, o1, o2);
+            }
+        }
+        return first ? (v.x & 0xFFFFu) : (v.x >> 16);
+    }
+
+    // pass 1 of add_segment (:230-314), literally from the root
+    __device__ bool search_from_root(uint32_t up, uint32_t lo) {
+        const float2 Pu = sxy[up], Pl = sxy[lo];
+        uint32_t base = 0, ncr = 0;
+        nstack = 0;
+        for (;;) {      // loop1 :231
+            for (;;) {  // loop :232
+                const uint2 v = nd[base];
+                if (type_of(v.y) == T_TRAPEZOID) break;
+                bool both;
+                const uint32_t next = dfs_step(v, up, lo, Pu, Pl, &both);
+                if (both) cstack[ncr++] = (uint16_t)base;
+                base = next;
+            }
+            if (!push(base)) return false;  // :302
+            if (ncr == 0) break;            // :306-313
+            base = nd[cstack[--ncr]].x >> 16;
+        }
+        return true;
+    }
+
+    // pass 2 of add_segment (:316-395) on node_stack; p1 is the rank id of the edge's first point
+    __device__ bool pass2(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
+        // The two open trapezoids live in registers until they are closed.
+        uint32_t left = alloc();
+        if (left == FNIL) return false;
+        uint32_t right = alloc();
+        if (right == FNIL) return false;
+        const uint32_t fresh = FNIL | (FNIL << 16);
+        uint32_t lx = fresh, ly = up | (T_TRAPEZOID << 14) | (FNIL << 16);
+        uint32_t rx = fresh, ry = ly;
+        const bool crumb_left = (p1 == up);  // :351
+        while (nstack > 0) {                 // :325
+            // :329-337: the entry with the highest point2 (lowest rank) strictly above `low`; ties and
+            // "none" resolve to the lowest index -> arg-min over (rank << 16 | index)
+            uint32_t base_index = 0, low = lo;
+            if (nstack <= serial_below) {  // short stack: the scan as written
+                for (uint32_t i = 0; i < nstack; ++i) {
+                    const uint32_t np = nd[stack[i]].y >> 16;
+                    if (np == FNIL) {  // :330 `.?`
+                        status |= MR_POLY_NULL_UNWRAP;
+                        return false;
+                    }
+                    if (np < low) {
+                        low = np;
+                        base_index = i;
+                    }
+                }
+            } else {
+                uint32_t best = 0xFFFFFFFFu;
+                bool null_p2 = false;
+                for (uint32_t i = lane; i < nstack; i += 32) {
+                    const uint32_t np = nd[stack[i]].y >> 16;
+                    null_p2 = null_p2 || (np == FNIL);
+                    best = min(best, (np << 16) | i);
+                }
+                if (__any_sync(0xFFFFFFFFu, null_p2)) {  // :330 `.?`
+                    status |= MR_POLY_NULL_UNWRAP;
+                    return false;
+                }
+                best = __reduce_min_sync(0xFFFFFFFFu, best);
+                if ((best >> 16) < lo) {
+                    low = best >> 16;
+                    base_index = best & 0xFFFFu;
+                }
+            }
+            const uint32_t base_id = stack[base_index];
+            const uint32_t bch = nd[base_id].x;  // :347-360
+            lx = (lx & 0xFFFF0000u) | (bch & 0xFFFFu);
+            rx = (rx & 0x0000FFFFu) | (bch & 0xFFFF0000u);
+            __syncwarp();
+            nd[base_id] = make_uint2(left | (right << 16), up | (T_SEGMENT << 14) | (lo << 16));
+            crumb[base_id] = (uint16_t)(crumb_left ? left : right);
+            if (lo == low) {  // :366-373
+                lx = (lx & 0xFFFFu) | (base_id << 16);
+                ly = (ly & 0xFFFFu) | (low << 16);
+                rx = (rx & 0xFFFF0000u) | base_id;
+                ry = (ry & 0xFFFFu) | (low << 16);
+                break;
+            } else if (left_of(sxy[low], up, lo)) {  // :375-382
+                lx = (lx & 0xFFFFu) | (base_id << 16);
+                ly = (ly & 0xFFFFu) | (low << 16);
+                nd[left] = make_uint2(lx, ly);
+                crumb[left] = (uint16_t)FNIL;
+                left = alloc();
+                if (left == FNIL) return false;
+                lx = fresh;
+                ly = low | (T_TRAPEZOID << 14) | (FNIL << 16);
+            } else {  // :383-391
+                rx = (rx & 0xFFFF0000u) | base_id;
+                ry = (ry & 0xFFFFu) | (low << 16);
+                nd[right] = make_uint2(rx, ry);
+                crumb[right] = (uint16_t)FNIL;
+                right = alloc();
+                if (right == FNIL) return false;
+                rx = fresh;
+                ry = low | (T_TRAPEZOID << 14) | (FNIL << 16);
+            }
+            stack[base_index] = stack[nstack - 1];  // :394
+            --nstack;
+            __syncwarp();
+        }
+        nd[left] = make_uint2(lx, ly);
+        crumb[left] = (uint16_t)FNIL;
+        nd[right] = make_uint2(rx, ry);
+        crumb[right] = (uint16_t)FNIL;
+        return true;
+    }
+};
+
+// All 32 lanes call this.  Returns F_DONE with *res filled, or a requeue code.
+__device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps,
+                                    const FLayout L, Result* res) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint64_t p0 = a.first_point[pi] - a.point_base;
+    const uint64_t np64 = a.first_point[pi + 1] - a.first_point[pi];
+    const uint64_t t0 = a.first_tri[pi] - a.tri_base;
+    const uint32_t cap_tri = (uint32_t)(a.first_tri[pi + 1] - a.first_tri[pi]);
+    const uint32_t n = (uint32_t)(np64 > 0xFFFFFFFFull ? 0xFFFFFFFFull : np64);
+
+    Sink sink;
+    sink.base = a.vtx_out + t0 * 3u * a.stride;
+    sink.cap_vtx = cap_tri * 3u;
+    sink.stride = a.stride;
+    sink.off_x = a.off_x;
+    sink.off_c = a.off_c;
+    sink.fast32 = a.fast32;
+
+    res->status = MR_POLY_OK;
+    res->ntri = 0;
+    res->b1x = res->b1y = res->b2x = res->b2y = 0.0f;
+    res->requeue = false;
+
+    if (n < 3u) {
+        res->status = MR_POLY_DEGENERATE;
+        sink.zero(0, sink.cap_vtx, lane);
+        return F_DONE;
+    }
+    if (n > MR_MAX_POLYGON_POINTS) {
+        res->status = MR_POLY_TOO_LARGE;
+        sink.zero(0, sink.cap_vtx, lane);
+        return F_DONE;
+    }
+    if (n > caps.nmax) return F_REQUEUE_GENERAL;
+
+    float2* sxy = reinterpret_cast<float2*>(ws + L.sxy);
+    uint16_t* orig = reinterpret_cast<uint16_t*>(ws + L.orig);
+    uint16_t* rk = reinterpret_cast<uint16_t*>(ws + L.rk);
+    uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
+
+    // ---- load, validate, rank -------------------------------------------------------------------
+    // Original coordinates are staged in the node arena (free until the trapezoidation starts).
+    float2* raw = reinterpret_cast<float2*>(ws + L.nodes);
+    bool finite = true;
+    {
+        const float2* src = reinterpret_cast<const float2*>(a.xy) + p0;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const float2 v = __ldg(src + i);
+            raw[i] = v;
+            finite = finite && isfinite(v.x) && isfinite(v.y);
+        }
+    }
+    __syncwarp();
+    if (!__all_sync(0xFFFFFFFFu, finite)) {
+        res->status = MR_POLY_NONFINITE;
+        sink.zero(0, sink.cap_vtx, lane);
+        return F_DONE;
+    }
+    bool tie = false;
+    for (uint32_t i = lane; i < n; i += 32) {  // rank = number of points strictly above (y, x)
+        const float2 me = raw[i];
+        uint32_t r = 0;
+        for (uint32_t q = 0; q < n; ++q) {
+            const float2 o = raw[q];
+            r += ((o.y < me.y) || (o.y == me.y && o.x < me.x)) ? 1u : 0u;
+            tie = tie || (q != i && o.y == me.y && o.x == me.x);
+        }
+        rk[i] = (uint16_t)r;
+    }
+    if (__any_sync(0xFFFFFFFFu, tie)) return F_REQUEUE_GENERAL;  // coincident points: general path
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t r = rk[i];
+        sxy[r] = raw[i];
+        orig[r] = (uint16_t)i;
+        loc[i] = 0;  // every point starts at the root
+    }
+    __syncwarp();
+
+    // ---- unirand (unirand.zig:12-50) -------------------------------------------------------------
+    uint32_t ur_offset, ur_prime;
+    if (a.offset_prime) {
+        ur_offset = __ldg(a.offset_prime + 2 * (size_t)pi);
+        ur_prime = __ldg(a.offset_prime + 2 * (size_t)pi + 1);
+    } else {
+        unirand_seed_warp(n, a.seed, a.poly_index0 + pi, lane, &ur_offset, &ur_prime);
+    }
+
+    // ---- part 1: trapezoidation ---------------------------------------------------------------------
+    FPoly P;
+    P.sxy = sxy;
+    P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
+    P.crumb = reinterpret_cast<uint16_t*>(ws + L.crumb);
+    P.stack = reinterpret_cast<uint16_t*>(ws + L.stack);
+    P.cstack = reinterpret_cast<uint16_t*>(ws + L.cstack);
+    P.nnodes = 1;  // :479 root trapezoid
+    P.nstack = 0;
+    P.status = MR_POLY_OK;
+    P.spec_node_cap = MR_NODE_CAP(n);
+    P.spec_stack_cap = MR_STACK_CAP(n);
+    P.tier_node_cap = caps.node_cap;
+    P.tier_stack_cap = caps.stack_cap;
+    P.requeue = false;
+    P.nd[0] = make_uint2(FNIL | (FNIL << 16), FNIL14 | (T_TRAPEZOID << 14) | (FNIL << 16));
+    P.crumb[0] = (uint16_t)FNIL;
+    __syncwarp();
+
+    // ---- conflict lists of the pending edges (items tier) ---------------------------------------------
+    const bool use_items = caps.item_cap != 0 && !(a.tune & 1u);
+    const uint32_t item_period = (((a.tune >> 1) & 15u) ? ((a.tune >> 1) & 15u) : 4u) * ((n + 63u) / 64u);
+    uint16_t* it_node = reinterpret_cast<uint16_t*>(ws + L.it_node);
+    uint16_t* it_next = reinterpret_cast<uint16_t*>(ws + L.it_next);
+    uint16_t* it_edge = reinterpret_cast<uint16_t*>(ws + L.it_edge);
+    uint16_t* ehead = reinterpret_cast<uint16_t*>(ws + L.ehead);
+    uint32_t* eul = reinterpret_cast<uint32_t*>(ws + L.eul);
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(ws + L.ctr);  // [0] items allocated, [1] pool overflow flag
+    if (use_items) {
+        for (uint32_t e = lane; e < n; e += 32) {  // every edge starts with one item at the root
+            const uint32_t pa = rk[e], pb = rk[e + 1u == n ? 0u : e + 1u];
+            eul[e] = min(pa, pb) | (max(pa, pb) << 16);  // (upper, lower)  :218-224
+            it_node[e] = 0;
+            it_next[e] = (uint16_t)FNIL;
+            it_edge[e] = (uint16_t)e;
+            ehead[e] = (uint16_t)e;
+        }
+        if (lane == 0) {
+            ctr[0] = n;
+            ctr[1] = 0;
+        }
+    }
+    __syncwarp();
+
+    const uint32_t refresh_every = (n + 63u) / 64u;
+    bool ok = true;
+    for (uint32_t at = 0; at < n && ok; ++at) {  // :484-494
+        if (at % refresh_every == 0) {
+            // lane-parallel advance of every pending point's cached location (loc is in rank space)
+            for (uint32_t r = lane; r < n; r += 32) {
+                const uint32_t cur = loc[r];
+                if (cur != FNIL) loc[r] = (uint16_t)P.locate(r, sxy[r], cur);  // never FNIL: r is not inserted yet
+            }
+            if (use_items && (at % item_period == 0)) {
+                // lane-parallel advance of every pending edge's search; new sibling items are handled in
+                // the next round
+                uint32_t start = 0, end = ctr[0];
+                while (start < end) {
+                    for (uint32_t it = start + lane; it < end; it += 32) {
+                        const uint32_t e = it_edge[it];
+                        if (ehead[e] == FNIL) continue;  // edge already inserted
+                        uint32_t node = it_node[it];
+                        uint2 v = P.nd[node];
+                        if (FPoly::type_of(v.y) == T_TRAPEZOID) continue;
+                        const uint32_t ul = eul[e];
+                        const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
+                        const float2 Pu = sxy[up], Pl = sxy[lo];
+                        do {
+                            bool both;
+                            const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
+                            if (both) {
+                                const uint32_t nw = atomicAdd(&ctr[0], 1u);
+                                if (nw >= caps.item_cap) {
+                                    ctr[1] = 1;
+                                    break;
+                                }
+                                it_node[nw] = (uint16_t)(v.x >> 16);  // child2, searched after everything under child1
+                                it_edge[nw] = (uint16_t)e;
+                                it_next[nw] = it_next[it];
+                                it_next[it] = (uint16_t)nw;
+                            }
+                            node = next;
+                            v = P.nd[node];
+                        } while (FPoly::type_of(v.y) != T_TRAPEZOID);
+                        it_node[it] = (uint16_t)node;
+                    }
+                    __syncwarp();
+                    start = end;
+                    end = min(ctr[0], caps.item_cap);
+                }
+                if (ctr[1]) {  // pool exhausted: the next tier redoes this polygon with the literal search
+                    P.requeue = true;
+                    break;
+                }
+            }
+            __syncwarp();
+        }
+        const uint32_t edge = (uint32_t)(at * ur_prime + ur_offset) % n;
+        const uint32_t p1 = rk[edge];
+        const uint32_t p2 = rk[edge + 1u == n ? 0u : edge + 1u];
+        const uint32_t up = min(p1, p2), lo = max(p1, p2);  // :218-224 in rank space
+        // add_point(p1), add_point(p2)  :489-490
+#pragma unroll
+        for (int which = 0; which < 2 && ok; ++which) {
+            const uint32_t pid = which ? p2 : p1;
+            const uint32_t cur = loc[pid];
+            if (cur != FNIL) {  // not inserted yet (an inserted point's walk ends at its own node, :149-152)
+                const uint32_t leaf = P.locate(pid, sxy[pid], cur);
+                ok = P.split(leaf, pid);
+                loc[pid] = (uint16_t)FNIL;
+            }
+        }
+        if (!ok) break;
+        // add_segment(p1, p2)  :493 -- pass 1
+        if (use_items) {
+            // finish this edge's search (its own two points were inserted a moment ago) and copy the
+            // leaves, in list order, into node_stack
+            P.nstack = 0;
+            const float2 Pu = sxy[up], Pl = sxy[lo];
+            uint32_t it = ehead[edge];
+            while (it != FNIL && ok) {
+                uint32_t node = it_node[it];
+                uint32_t nxt = it_next[it];
+                for (;;) {
+                    const uint2 v = P.nd[node];
+                    if (FPoly::type_of(v.y) == T_TRAPEZOID) break;
+                    bool both;
+                    const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
+                    if (both) {
+                        const uint32_t nw = ctr[0];
+                        if (nw >= caps.item_cap) {
+                            P.requeue = true;
+                            ok = false;
+                            break;
+                        }
+                        __syncwarp();
+                        if (lane == 0) ctr[0] = nw + 1u;
+                        it_node[nw] = (uint16_t)(v.x >> 16);
+                        it_edge[nw] = (uint16_t)edge;
+                        it_next[nw] = (uint16_t)nxt;
+                        nxt = nw;
+                        __syncwarp();
+                    }
+                    node = next;
+                }
+                if (!ok) break;
+                ok = P.push(node);  // :302
+                it = nxt;
+            }
+            ehead[edge] = (uint16_t)FNIL;
+            if (!ok) break;
+        } else {
+            ok = P.search_from_root(up, lo);
+            if (!ok) break;
+        }
+        ok = P.pass2(p1, up, lo, lane, ((a.tune >> 8) & 31u) ? ((a.tune >> 8) & 31u) : 16u);  // pass 2
+        __syncwarp();
+    }
+    if (P.requeue) return F_REQUEUE_SPEC;
+    if (!ok) {
+        res->status = P.status | (sink.cap_vtx ? MR_POLY_UNDERFILL : 0u);
+        sink.zero(0, sink.cap_vtx, lane);
+        return F_DONE;
+    }
+
+    // ---- part 2: inside trapezoids -> adds, in node id order (:510-540) ---------------------------
+    uint32_t* add_pp = reinterpret_cast<uint32_t*>(ws + L.add_pp);
+    uint32_t* add_key = reinterpret_cast<uint32_t*>(ws + L.add_key);
+    uint16_t* add_m = reinterpret_cast<uint16_t*>(ws + L.add_m);
+    uint32_t* mcount = reinterpret_cast<uint32_t*>(ws + L.mcount);
+    uint16_t* mstart = reinterpret_cast<uint16_t*>(ws + L.mstart);
+    uint16_t* efirst = reinterpret_cast<uint16_t*>(ws + L.efirst);
+    const uint32_t PMASK = 0xFFFF3FFFu;  // (pa, pb) without the type bits
+
+    uint32_t A = 0;
+    bool bad = false, over = false;
+    for (uint32_t b = 0; b < P.nnodes; b += 32) {
+        const uint32_t id = b + lane;
+        uint32_t cnt = 0, k0 = 0, k1 = 0, mypp = 0;
+        bool lane_bad = false;
+        if (id < P.nnodes) {
+            const uint2 v = P.nd[id];
+            if (FPoly::type_of(v.y) == T_TRAPEZOID) {
+                const uint32_t c1 = v.x & 0xFFFFu, c2 = v.x >> 16;
+                if (c1 != FNIL) {                                    // :516
+                    if (P.crumb[c1] == (P.nd[c1].x >> 16)) {         // :517 crumb == child2
+                        mypp = v.y & PMASK;
+                        if ((mypp & FNIL14) == FNIL14 || (mypp >> 16) == FNIL || c2 == FNIL) {
+                            lane_bad = true;  // :524-527
+                        } else {
+                            const uint32_t c2pp = P.nd[c2].y & PMASK, c1pp = P.nd[c1].y & PMASK;
+                            if (mypp == c2pp) {  // :528
+                                cnt = 1;
+                                k0 = c1pp;
+                            } else if (mypp == c1pp) {  // :531
+                                cnt = 1;
+                                k0 = c2pp;
+                            } else {  // :534-538
+                                cnt = 2;
+                                k0 = c1pp;
+                                k1 = c2pp;
+                            }
+                            if ((k0 & FNIL14) == FNIL14 || (k0 >> 16) == FNIL) lane_bad = true;  // :58
+                            if (cnt == 2 && ((k1 & FNIL14) == FNIL14 || (k1 >> 16) == FNIL)) lane_bad = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, lane_bad)) {
+            bad = true;
+            break;
+        }
+        const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, cnt >= 1);
+        const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, cnt == 2);
+        const uint32_t off = A + __popc(m1 & lt_mask) + __popc(m2 & lt_mask);
+        const uint32_t total = __popc(m1) + __popc(m2);
+        if (A + total > caps.add_cap) {
+            over = true;
+            break;
+        }
+        if (cnt >= 1) {
+            add_key[off] = k0;
+            add_pp[off] = mypp;
+        }
+        if (cnt == 2) {
+            add_key[off + 1] = k1;
+            add_pp[off + 1] = mypp;
+        }
+        A += total;
+    }
+    if (over) return F_REQUEUE_SPEC;  // more adds than this tier holds (the kernel maps this to the next tier up)
+    if (bad) {
+        res->status = MR_POLY_NULL_UNWRAP | (sink.cap_vtx ? MR_POLY_UNDERFILL : 0u);
+        sink.zero(0, sink.cap_vtx, lane);
+        return F_DONE;
+    }
+    __syncwarp();
+
+    // ---- mountains: rank by first appearance (keys are (upper, lower) rank pairs) ----------------
+    for (uint32_t i = lane; i < n; i += 32) efirst[i] = (uint16_t)FNIL;
+    __syncwarp();
+    uint32_t M = 0;
+    for (uint32_t b = 0; b < A; b += 32) {
+        const uint32_t ai = b + lane;
+        const bool valid = ai < A;
+        const uint32_t key = valid ? add_key[ai] : 0u;
+        const uint32_t ku = key & FNIL14, kl = key >> 16;
+        uint32_t e = FNIL;
+        if (valid && ku < n && kl < n && ku < kl) {  // (upper, lower) of a polygon edge?
+            const uint32_t ou = orig[ku], ol = orig[kl];
+            if ((ou + 1u == n ? 0u : ou + 1u) == ol) e = ou;
+            else if ((ol + 1u == n ? 0u : ol + 1u) == ou) e = ol;
+        }
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, valid ? key : (0xC0000000u + lane));
+        const bool leader = valid && ((same & lt_mask) == 0u);
+        uint32_t first = ai;
+        if (leader) {
+            if (e != FNIL) {
+                const uint32_t f = efirst[e];
+                if (f != FNIL) first = f; else efirst[e] = (uint16_t)ai;
+            } else {
+                for (uint32_t h = 0; h < b; ++h)  // rare: the key node is not a segment of the polygon
+                    if (add_key[h] == key) {
+                        first = h;
+                        break;
+                    }
+            }
+        }
+        first = __shfl_sync(0xFFFFFFFFu, first, __ffs(same) - 1);
+        const bool isfirst = valid && first == ai;
+        const uint32_t fm = __ballot_sync(0xFFFFFFFFu, isfirst);
+        // first adds store their mountain rank with bit 15 set; the others the index of the first add
+        if (valid) add_m[ai] = (uint16_t)(isfirst ? (0x8000u | (M + __popc(fm & lt_mask))) : first);
+        M += __popc(fm);
+        __syncwarp();
+    }
+    for (uint32_t ai = lane; ai < A; ai += 32) {
+        const uint32_t v = add_m[ai];
+        if (!(v & 0x8000u)) add_m[ai] = (uint16_t)(add_m[v] & 0x7FFFu);  // add_m[v] is a first add, never rewritten here
+    }
+    __syncwarp();
+    for (uint32_t ai = lane; ai < A; ai += 32) add_m[ai] &= 0x7FFFu;
+    for (uint32_t i = lane; i < M; i += 32) mcount[i] = 0u;
+    __syncwarp();
+    for (uint32_t ai = lane; ai < A; ai += 32) atomicAdd(&mcount[add_m[ai]], 2u);
+    __syncwarp();
+    {
+        uint32_t run = 0;
+        for (uint32_t b = 0; b < M; b += 32) {
+            const uint32_t i = b + lane;
+            const uint32_t v = i < M ? mcount[i] : 0u;
+            uint32_t inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if ((int)lane >= d) inc += t;
+            }
+            if (i < M) mstart[i] = (uint16_t)(run + inc - v);
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) mstart[M] = (uint16_t)run;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < M; i += 32) mcount[i] = 0u;
+    __syncwarp();
+
+    // ---- group entries by mountain, stable sort by (rank, append position)  (:555) ----------------
+    // sort arrays alias the node arena: Gpos, cum, Gid, Gm, S -- u16 each, E = 2A entries
+    const uint32_t E = 2u * A;
+    const size_t ecap = (size_t)caps.add_cap * 2;
+    uint16_t* Gpos = reinterpret_cast<uint16_t*>(ws + L.nodes);
+    uint16_t* cum = Gpos + ecap;
+    uint16_t* Gid = cum + ecap;
+    uint16_t* Gm = Gid + ecap;
+    uint16_t* S = Gm + ecap;
+    for (uint32_t ai = lane; ai < A; ai += 32) {
+        const uint32_t m = add_m[ai];
+        const uint32_t pp = add_pp[ai];
+        const uint32_t slot = mstart[m] + atomicAdd(&mcount[m], 2u);
+        Gpos[slot] = (uint16_t)(2u * ai);  // p1 appended first (:60)
+        Gid[slot] = (uint16_t)(pp & FNIL14);
+        Gpos[slot + 1] = (uint16_t)(2u * ai + 1u);  // then p2 (:61)
+        Gid[slot + 1] = (uint16_t)(pp >> 16);
+        Gm[slot] = (uint16_t)m;
+        Gm[slot + 1] = (uint16_t)m;
+    }
+    __syncwarp();
+    for (uint32_t g = lane; g < E; g += 32) {
+        const uint32_t m = Gm[g];
+        const uint32_t s = mstart[m], t = mstart[m + 1];
+        const uint32_t mykey = ((uint32_t)Gid[g] << 16) | Gpos[g];  // (rank, append position)
+        uint32_t rank = 0;
+        for (uint32_t h = s; h < t; ++h) rank += ((((uint32_t)Gid[h] << 16) | Gpos[h]) < mykey) ? 1u : 0u;
+        S[s + rank] = Gid[g];
+    }
+    __syncwarp();
+
+    // ---- triangles: valid j, acute check, slots  (:558-586 in closed form) -------------------------
+    uint32_t running = 0;
+    bool all_acute = true;
+    for (uint32_t b = 0; b < E; b += 32) {
+        const uint32_t g = b + lane;
+        bool valid = false;
+        if (g < E) {
+            const uint32_t s = mstart[Gm[g]];
+            if (g >= s + 2u) {
+                const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
+                valid = (c != a1) && (c != a2);
+                if (valid && !is_acute(sxy, c, a1, a2)) all_acute = false;
+            }
+        }
+        const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+        if (g < E) cum[g] = (uint16_t)(running + __popc(vm & (lt_mask | (1u << lane))));
+        running += __popc(vm);
+    }
+    all_acute = __all_sync(0xFFFFFFFFu, all_acute);
+    __syncwarp();
+
+    if (all_acute) {
+        const uint32_t T = running;
+        float mn = 0.0f, mx = 0.0f, lasty = 0.0f;
+        bool has_last = false;
+        for (uint32_t g = lane; g < E; g += 32) {
+            const uint32_t m = Gm[g];
+            const uint32_t s = mstart[m], t = mstart[m + 1];
+            if (g < s + 2u) continue;
+            const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
+            if (c == a1 || c == a2) continue;
+            const uint32_t before = s ? cum[s - 1] : 0u;
+            const uint32_t slot = before + (cum[t - 1] - cum[g]);
+            // the emit order (:405-422) is defined on the original point ids
+            const uint32_t oc = orig[c], o1 = orig[a1], o2 = orig[a2];
+            uint32_t second, third;
+            if ((o1 > oc && o2 > oc) || (o1 < oc && o2 < oc)) {
+                second = o1 > o2 ? a2 : a1;
+                third = o1 > o2 ? a1 : a2;
+            } else if (o2 > oc) {
+                second = a2;
+                third = a1;
+            } else {
+                second = a1;
+                third = a2;
+            }
+            const float2 q0 = sxy[c], q1 = sxy[second], q2 = sxy[third];
+            mn = fmin_acc(fmin_acc(fmin_acc(mn, q0.x), q1.x), q2.x);
+            mx = fmax_acc(fmax_acc(fmax_acc(mx, q0.x), q1.x), q2.x);
+            if (slot == T - 1u) {
+                lasty = q2.y;
+                has_last = true;
+            }
+            if (slot < cap_tri) {
+                sink.write(3u * slot, q0);
+                sink.write(3u * slot + 1u, q1);
+                sink.write(3u * slot + 2u, q2);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            mn = fmin_acc(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+            mx = fmax_acc(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+        }
+        {
+            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, has_last);
+            lasty = lm ? __shfl_sync(0xFFFFFFFFu, lasty, __ffs(lm) - 1) : 0.0f;
+        }
+        uint32_t status = MR_POLY_OK;
+        if (T > cap_tri) status |= MR_POLY_OVERFLOW;
+        if (T < cap_tri) {
+            status |= MR_POLY_UNDERFILL;
+            sink.zero(3u * T, sink.cap_vtx, lane);
+        }
+        res->b1x = mn;
+        res->b2x = mx;
+        res->b1y = T ? fmin_acc(mn, lasty) : 0.0f;
+        res->b2y = T ? fmax_acc(mx, lasty) : 0.0f;
+        res->status = status;
+        res->ntri = T < cap_tri ? T : cap_tri;
+        return F_DONE;
+    }
+    // a push_triangle_if_acute returned false somewhere: the literal loop of the general path decides
+    return F_REQUEUE_GENERAL;
+}
