@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", action="store_true",
+                    help="N>1: also time building the terrain bands straight into rank 0's buffer over NVLink (IPC peer stores)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -323,6 +325,53 @@ def main():
                "d2h_poly": h_pvtx.numel() + h_bbox.numel() * 4 + h_stat.numel() * 4 + h_ntri.numel() * 4,
                "status_ok": int((h_stat.numpy() == 0).sum())}
 
+    # ---- N>1: gather into rank 0's buffer by NVLink peer stores (reported separately) -----------------
+    gather = None
+    if world > 1 and args.gather:
+        try:
+            total_bytes = n * n * STRIDE
+            handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+            base = C.c_void_p()
+            if rank == 0:
+                ctx.check(lib.mr_device_alloc(ctx.handle, total_bytes, C.byref(base)), "alloc gather buffer")
+                hb = (C.c_ubyte * 64)()
+                ctx.check(lib.mr_ipc_export(ctx.handle, base, hb), "ipc export")
+                handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+            dist.broadcast(handle, src=0)
+            if rank != 0:
+                hb = (C.c_ubyte * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
+                ctx.check(lib.mr_ipc_open(ctx.handle, hb, C.byref(base)), "ipc open")
+            job_g = T.job(height, n, rows=(r0, r1), qrows=(q0, q0), height_row0=lo, height_rows=hi - lo,
+                          vtx_out=base.value, vtx_row0=0)  # global row origin: the band lands at its final offset
+            for _ in range(2):
+                T.build(job_g)
+            barrier()
+            tg = []
+            for _ in range(max(3, min(args.steps, 10))):
+                a, b = ev(), ev()
+                a.record()
+                T.build(job_g)  # rank g > 0: every vertex store crosses NVLink into rank 0's HBM
+                b.record()
+                torch.cuda.synchronize()
+                tg.append(a.elapsed_time(b))
+                barrier()
+            ms_g = sum(tg) / len(tg)
+            ok_gather = True
+            if rank == 0:  # spot-check: the last band (written by the last rank over NVLink) is non-zero
+                chk = torch.empty(1024, dtype=torch.uint8, device=dev)
+                ctx.check(lib.mr_copy(ctx.handle, chk.data_ptr(), base.value + total_bytes - 1024, 1024), "copy")
+                ctx.sync()
+                ok_gather = bool(chk.any().item())
+            gather = {"ms": ms_g, "ok": ok_gather}
+            barrier()
+            if rank != 0:
+                lib.mr_ipc_close(ctx.handle, base)
+            barrier()
+            if rank == 0:
+                lib.mr_device_free(ctx.handle, base)
+        except Exception as exc:  # the gather figure is informative; never lose the main line over it
+            gather = {"error": str(exc)[:200]}
+
     # ---- reduce over ranks: max time, sum of units ------------------------------------------------
     def reduce_max(x):
         if world == 1:
@@ -352,6 +401,8 @@ def main():
         e_h2d = int(reduce_sum(e2e["h2d_terrain"] + e2e["h2d_poly"]))
         e_d2h = int(reduce_sum(e2e["d2h_terrain"] + e2e["d2h_poly"]))
     ok_total = reduce_sum(int((pstat == 0).sum().item()))
+    if gather is not None and "ms" in gather:
+        gather["ms"] = reduce_max(gather["ms"])
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -387,6 +438,12 @@ def main():
                            "h2d_bytes_per_step": e_h2d, "d2h_bytes_per_step": e_d2h, "ms_terrain": e_ms_t,
                            "ms_polygons": e_ms_p, "polygons_per_s": polys_total / (e_ms_p * 1e-3),
                            "path": "mr_terrain_build / mr_triangulate_batch with pinned host buffers"}
+        if gather is not None:
+            if "ms" in gather:
+                nv_bytes = n * n * STRIDE * (world - 1) / world
+                gather.update({"what": "terrain vertex bands stored directly into rank 0's buffer (IPC-mapped peer pointer)",
+                               "nvlink_bytes": int(nv_bytes), "rank0_ingest_gb_per_s": nv_bytes / (gather["ms"] * 1e-3) / 1e9})
+            line["gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O  # CPU baseline leg only
 
