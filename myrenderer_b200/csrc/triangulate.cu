@@ -26,10 +26,11 @@ namespace {
 
 constexpr uint32_t NIL = 0xFFFFu;
 enum : uint32_t { T_POINT = 0, T_SEGMENT = 1, T_TRAPEZOID = 2 };
-constexpr int NUM_CLASSES = 8;  // 0..6: n <= 16,32,...,1024 (shared memory); 7: up to MR_MAX (global)
+constexpr int NUM_CLASSES = 6;  // tiers 0..4: n <= 64,128,256,512,1024 (shared memory); 5: up to MR_MAX (global)
+constexpr int NBINS = MR_MAX_POLYGON_POINTS + 1;  // polygons are queued by exact size, largest first
 constexpr int MAX_WARPS_PER_BLOCK = 4;
 
-__host__ __device__ inline uint32_t class_nmax(int c) { return 16u << c; }
+__host__ __device__ inline uint32_t class_nmax(int c) { return 64u << c; }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
     while (c < NUM_CLASSES - 1 && n > class_nmax(c)) ++c;
@@ -107,7 +108,8 @@ struct BatchArgs {
     uint32_t tune;                  // experiment knobs (MR_TUNE), see triangulate_fast.cuh
     // work lists
     const uint32_t* order;        // polygon ids grouped by class
-    const uint32_t* class_begin;  // NUM_CLASSES+1
+    const uint32_t* class_begin;  // NUM_CLASSES: first position of the class in `order` (sorted by size, descending)
+    const uint32_t* class_end;    // NUM_CLASSES
     uint32_t* queue_head;         // [0,8): fast tier per class; [8,16): spec tier per class; [16,18): general
     uint32_t* spec_list;          // npoly, class c's overflow at class_begin[c]..
     uint32_t* spec_count;         // NUM_CLASSES
@@ -1030,14 +1032,14 @@ __device__ __forceinline__ void write_result(const BatchArgs& a, uint32_t pi, co
 // ---- kernels ----------------------------------------------------------------------------------
 // Fast path, class c, shared-memory workspace.  spec == 0: the class's polygons with arenas sized for
 // the typical case; spec == 1: the polygons that outgrew those, with arenas at the contract caps.
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32, 6) triangulate_fast_k(const BatchArgs a, int c, int spec) {
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(const BatchArgs a, int c, int spec) {
     extern __shared__ __align__(16) unsigned char smem[];
     const FCaps caps = fast_caps(c, spec != 0);
     const FLayout L = fast_layout(caps);
     unsigned char* ws = smem + (size_t)(threadIdx.x >> 5) * L.total;  // blockDim.x/32 warps per block
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t begin = a.class_begin[c];
-    const uint32_t count = spec ? a.spec_count[c] : (a.class_begin[c + 1] - begin);
+    const uint32_t count = spec ? a.spec_count[c] : (a.class_end[c] - begin);
     const uint32_t* list = spec ? a.spec_list : a.order;
     uint32_t* head = spec ? &a.queue_head[NUM_CLASSES + c] : &a.queue_head[c];
     for (;;) {
@@ -1071,7 +1073,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_general_
     unsigned char* ws = a.tier1_ws + (size_t)warp_global * a.tier1_ws_stride;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t c = NUM_CLASSES - 1;
-    const uint32_t begin = a.class_begin[c], end = a.class_begin[c + 1];
+    const uint32_t begin = a.class_begin[c], end = a.class_end[c];
     const uint32_t total = which == 0 ? *a.general_count : (end - begin);
     for (;;) {
         uint32_t idx = 0;
@@ -1086,41 +1088,63 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_general_
     }
 }
 
-// work lists: class histogram, then scatter
-__global__ void classify_count_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
-                                 uint32_t* __restrict__ class_count) {
-    __shared__ uint32_t local[NUM_CLASSES];
-    if (threadIdx.x < NUM_CLASSES) local[threadIdx.x] = 0;
+// work lists: polygons sorted by size, largest first (counting sort on n), so that every tier's queue
+// hands out its most expensive polygons first and the kernel tail consists of the cheapest ones
+__device__ __forceinline__ uint32_t size_bin(uint64_t n) { return n > MR_MAX_POLYGON_POINTS ? 0u : (uint32_t)n; }  // invalid sizes ride in bin 0
+
+__global__ void __launch_bounds__(256) size_hist_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
+                                                  uint32_t* __restrict__ hist) {
+    __shared__ uint32_t local[NBINS];
+    for (uint32_t b = threadIdx.x; b < NBINS; b += blockDim.x) local[b] = 0;
     __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npoly; i += gridDim.x * blockDim.x) {
-        const uint64_t n = first_point[i + 1] - first_point[i];
-        const uint32_t nn = n > MR_MAX_POLYGON_POINTS ? 0u : (uint32_t)n;  // invalid sizes ride in class 0
-        atomicAdd(&local[class_of(nn)], 1u);
-    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npoly; i += gridDim.x * blockDim.x)
+        atomicAdd(&local[size_bin(first_point[i + 1] - first_point[i])], 1u);
     __syncthreads();
-    if (threadIdx.x < NUM_CLASSES && local[threadIdx.x]) atomicAdd(&class_count[threadIdx.x], local[threadIdx.x]);
+    for (uint32_t b = threadIdx.x; b < NBINS; b += blockDim.x)
+        if (local[b]) atomicAdd(&hist[b], local[b]);
 }
 
-__global__ void classify_scan_k(const uint32_t* __restrict__ class_count, uint32_t* __restrict__ class_begin,
-                                uint32_t* __restrict__ cursor) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int c = 0; c < NUM_CLASSES; ++c) {
-            class_begin[c] = acc;
-            cursor[c] = acc;
-            acc += class_count[c];
+// one block: cursor[b] = number of polygons with a size larger than b (descending order); class ranges
+__global__ void __launch_bounds__(1024) size_scan_k(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor,
+                                                   uint32_t* __restrict__ class_begin, uint32_t* __restrict__ class_end) {
+    __shared__ uint32_t part[1024];
+    constexpr int PER = (NBINS + 1023) / 1024;
+    // thread t owns bins NBINS-1-t*PER ... (descending)
+    uint32_t sum = 0;
+    for (int k = 0; k < PER; ++k) {
+        const int b = NBINS - 1 - (int)(threadIdx.x * PER + k);
+        if (b >= 0) sum += hist[b];
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan
+        const uint32_t v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (int k = 0; k < PER; ++k) {
+        const int b = NBINS - 1 - (int)(threadIdx.x * PER + k);
+        if (b >= 0) {
+            cursor[b] = run;
+            run += hist[b];
         }
-        class_begin[NUM_CLASSES] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_CLASSES) {
+        const int c = threadIdx.x;
+        const uint32_t hi = c == NUM_CLASSES - 1 ? MR_MAX_POLYGON_POINTS : class_nmax(c);  // largest size of the class
+        const uint32_t lo = c == 0 ? 0u : class_nmax(c - 1) + 1u;                          // smallest size
+        class_begin[c] = cursor[hi];
+        class_end[c] = cursor[lo] + hist[lo];
     }
 }
 
-__global__ void classify_scatter_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npoly; i += gridDim.x * blockDim.x) {
-        const uint64_t n = first_point[i + 1] - first_point[i];
-        const uint32_t nn = n > MR_MAX_POLYGON_POINTS ? 0u : (uint32_t)n;
-        order[atomicAdd(&cursor[class_of(nn)], 1u)] = i;
-    }
+__global__ void size_scatter_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
+                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npoly; i += gridDim.x * blockDim.x)
+        order[atomicAdd(&cursor[size_bin(first_point[i + 1] - first_point[i])], 1u)] = i;
 }
 
 __global__ void polygon_offsets_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
@@ -1221,30 +1245,31 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     const uint32_t npoly = j->npoly;
     if (npoly == 0) return MR_OK;
 
-    // work-list memory: a 64-word header followed by order[npoly], spec_list[npoly], general_list[npoly]
+    // work-list memory: header | hist[NBINS] | cursor[NBINS] | order[npoly] | spec_list[npoly] | general_list[npoly]
     const size_t header_words = 64;
     void* work = nullptr;
-    int rc = mr_scratch(ctx, SLOT_WORK, (header_words + 3 * (size_t)npoly) * 4, &work);
+    int rc = mr_scratch(ctx, SLOT_WORK, (header_words + 2 * (size_t)NBINS + 3 * (size_t)npoly) * 4, &work);
     if (rc) return rc;
     uint32_t* w = static_cast<uint32_t*>(work);
-    uint32_t* class_count = w;        // 8
-    uint32_t* class_begin = w + 8;    // 9
-    uint32_t* cursor = w + 18;        // 8
-    uint32_t* queue_head = w + 26;    // 18
-    uint32_t* spec_count = w + 44;    // 8
-    uint32_t* general_count = w + 52; // 1
-    uint32_t* order = w + header_words;
+    uint32_t* class_begin = w;        // NUM_CLASSES
+    uint32_t* class_end = w + 8;      // NUM_CLASSES
+    uint32_t* queue_head = w + 16;    // 2*NUM_CLASSES + 2
+    uint32_t* spec_count = w + 32;    // NUM_CLASSES
+    uint32_t* general_count = w + 40; // 1
+    uint32_t* hist = w + header_words;
+    uint32_t* cursor = hist + NBINS;
+    uint32_t* order = cursor + NBINS;
     uint32_t* spec_list = order + npoly;
     uint32_t* general_list = spec_list + npoly;
-    MR_CUDA(ctx, cudaMemsetAsync(w, 0, header_words * 4, ctx->stream));
+    MR_CUDA(ctx, cudaMemsetAsync(w, 0, (header_words + 2 * (size_t)NBINS) * 4, ctx->stream));
 
-    const unsigned cblocks = (unsigned)std::min<uint64_t>(((uint64_t)npoly + 255) / 256, (uint64_t)ctx->sm_count * 4);
-    classify_count_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, class_count);
-    MR_LAUNCH_CHECK(ctx, "classify_count_k");
-    classify_scan_k<<<1, 32, 0, ctx->stream>>>(class_count, class_begin, cursor);
-    MR_LAUNCH_CHECK(ctx, "classify_scan_k");
-    classify_scatter_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, cursor, order);
-    MR_LAUNCH_CHECK(ctx, "classify_scatter_k");
+    const unsigned cblocks = (unsigned)std::min<uint64_t>(((uint64_t)npoly + 255) / 256, (uint64_t)ctx->sm_count * 2);
+    size_hist_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, hist);
+    MR_LAUNCH_CHECK(ctx, "size_hist_k");
+    size_scan_k<<<1, 1024, 0, ctx->stream>>>(hist, cursor, class_begin, class_end);
+    MR_LAUNCH_CHECK(ctx, "size_scan_k");
+    size_scatter_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, cursor, order);
+    MR_LAUNCH_CHECK(ctx, "size_scatter_k");
 
     BatchArgs a;
     a.xy = j->xy;
@@ -1274,6 +1299,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     }
     a.order = order;
     a.class_begin = class_begin;
+    a.class_end = class_end;
     a.queue_head = queue_head;
     a.spec_list = spec_list;
     a.spec_count = spec_count;

@@ -48,7 +48,7 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
         k.add_cap = 2u * k.nmax + 16u;
         // conflict lists pay for themselves on larger polygons only (measured: 1.35-1.55x for n up to 1024,
         // a small loss for n <= 64 where the per-edge polling overhead exceeds the search it saves)
-        k.item_cap = c >= 3 ? 6u * k.nmax + 64u : 0u;  // 6 B per item >= the 16 B per add that reuse the pool later
+        k.item_cap = c >= 1 ? 6u * k.nmax + 64u : 0u;  // 6 B per item >= the 16 B per add that reuse the pool later
     } else {
         k.item_cap = 0;
         k.node_cap = MR_NODE_CAP(k.nmax);
@@ -111,12 +111,8 @@ struct FPoly {
     bool requeue;
 
     __device__ __forceinline__ uint32_t alloc() {
-        if (nnodes >= spec_node_cap) {
-            status |= MR_POLY_ARENA;
-            return FNIL;
-        }
-        if (nnodes >= tier_node_cap) {
-            requeue = true;
+        if (nnodes >= min(tier_node_cap, spec_node_cap)) {  // one compare on the hot path
+            if (nnodes >= spec_node_cap) status |= MR_POLY_ARENA; else requeue = true;
             return FNIL;
         }
         return nnodes++;
@@ -166,12 +162,8 @@ struct FPoly {
     }
 
     __device__ __forceinline__ bool push(uint32_t id) {
-        if (nstack >= spec_stack_cap) {
-            status |= MR_POLY_ARENA;
-            return false;
-        }
-        if (nstack >= tier_stack_cap) {
-            requeue = true;
+        if (nstack >= min(tier_stack_cap, spec_stack_cap)) {
+            if (nstack >= spec_stack_cap) status |= MR_POLY_ARENA; else requeue = true;
             return false;
         }
         stack[nstack++] = (uint16_t)id;
@@ -184,36 +176,30 @@ struct FPoly {
                                                   const float2 Pl, bool* both) const {
         const uint32_t pa = v.y & FNIL14;
         bool first;  // take child1
-        *both = false;
-        if (type_of(v.y) == T_POINT) {  // :234-259
-            if (up == pa) {
-                first = false;
-            } else if (lo == pa) {
-                first = true;
-            } else if (pa < up) {  // top_point_is_below
-                first = false;
-            } else if (lo < pa) {  // bottom_point_is_above
-                first = true;
-            } else {  // straddles: breadcrumb, then child1
-                *both = true;
-                first = true;
-            }
-        } else {  // :260-296
+        if (type_of(v.y) == T_POINT) {
+            // :234-259 collapsed.  As written: pa == up -> child2; pa == lo -> child1; pa above up -> child2;
+            // lo above pa -> child1; otherwise (up above pa above lo) breadcrumb + child1.  In rank space
+            // (up < lo, "above" is "<") that is exactly:
+            first = pa > up;
+            *both = first && (pa < lo);
+        } else {
+            // :260-296 with the five cases folded into operand selects (same tests, same operands)
+            *both = false;
             const uint32_t o1 = pa, o2 = v.y >> 16;
-            if (up == o2 || up == o1) {
-                first = left_of(Pl, o1, o2);
-            } else if (lo == o1 || lo == o2) {
-                first = left_of(Pu, o1, o2);
-            } else {
-                const bool top_is_above = up < o1;
-                const bool bottom_is_below = lo < o2;  // point_is_above(lower, other_p2), as written
-                if (top_is_above && bottom_is_below)
-                    first = !left_of(sxy[o1], up, lo);
-                else if (top_is_above)
-                    first = left_of(Pl, o1, o2);
-                else
-                    first = left_of(Pu, o1, o2);
-            }
+            const bool share_up = (up == o1) | (up == o2);                           // :266
+            const bool share_lo = (lo == o1) | (lo == o2);                           // :270
+            const bool top_is_above = up < o1;                                       // :275
+            const bool contained = !share_up & !share_lo & top_is_above & (lo < o2); // :277
+            const bool use_lower = share_up | (!share_lo & top_is_above);            // :269,:284 test the lower point
+            const float2 A = sxy[o1], B = sxy[o2];
+            const float2 Q = use_lower ? Pl : Pu;
+            // contained: !is_left_of(o1, up, lo) (:281); otherwise is_left_of(Q, o1, o2)
+            const float ax = contained ? Pu.x : A.x, ay = contained ? Pu.y : A.y;
+            const float bx = contained ? Pl.x : B.x, by = contained ? Pl.y : B.y;
+            const float px = contained ? A.x : Q.x, py = contained ? A.y : Q.y;
+            const float mul1 = __fmul_rn(__fsub_rn(bx, ax), __fsub_rn(py, ay));
+            const float mul2 = __fmul_rn(__fsub_rn(by, ay), __fsub_rn(px, ax));
+            first = (__fsub_rn(mul1, mul2) > 0.0f) != contained;
         }
         return first ? (v.x & 0xFFFFu) : (v.x >> 16);
     }
