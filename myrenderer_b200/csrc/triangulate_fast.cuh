@@ -43,14 +43,23 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
     FCaps k;
     k.nmax = class_nmax(c);
     if (!spec) {
-        k.node_cap = 6u * k.nmax + 16u;
-        k.stack_cap = k.nmax + 32u;
-        k.add_cap = 2u * k.nmax + 16u;
+        if (c == 0) {
+            // tier 0 is register-limited to 5 blocks/SM, which leaves ~11 KB of shared memory per warp:
+            // spend it on contract-cap node arenas and a deep stack so that almost no polygon needs the
+            // retry tier (whose separate launch is tail-bound)
+            k.node_cap = MR_NODE_CAP(k.nmax);
+            k.stack_cap = 4u * k.nmax + 64u;
+            k.add_cap = 3u * k.nmax + 32u;
+        } else {
+            k.node_cap = 6u * k.nmax + 16u;
+            k.stack_cap = k.nmax + 32u;
+            k.add_cap = 2u * k.nmax + 16u;
+        }
         // conflict lists pay for themselves on larger polygons only (measured: 1.35-1.55x for n up to 1024,
         // a small loss for n <= 64 where the per-edge polling overhead exceeds the search it saves)
         k.item_cap = c >= 1 ? 6u * k.nmax + 64u : 0u;  // 6 B per item >= the 16 B per add that reuse the pool later
     } else {
-        k.item_cap = 0;
+        k.item_cap = 0;  // measured: conflict lists slow the retry tier down (8.1 vs 6.1 ms on the 100k star batch)
         k.node_cap = MR_NODE_CAP(k.nmax);
         k.stack_cap = MR_STACK_CAP(k.nmax);
         k.add_cap = 4u * k.nmax + 32u;  // sort arrays (20 B per add) alias the node arena (10 B per node)
