@@ -227,6 +227,11 @@ typedef struct mr_polygon_job {
 } mr_polygon_job;
 
 int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job);
+/* Introspection: how the last mr_triangulate_batch on this context spread its polygons over the
+ * arena tiers.  out[0..5] = polygons re-run with contract-cap arenas, per size tier (<=64,128,...,1024,
+ * >1024); out[6] = polygons handed to the general path (coincident points, not-acute corner, ...);
+ * out[7] = polygons of the >1024 tier.  Synchronises the stream. */
+int mr_triangulate_tier_counts(mr_context* ctx, uint32_t out[8]);
 /* first_tri[0..npoly] from first_point[0..npoly] (device or host pointers). */
 int mr_polygon_offsets(mr_context* ctx, const uint64_t* first_point, uint32_t npoly,
                        uint64_t* first_tri_out);

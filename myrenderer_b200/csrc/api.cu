@@ -9,6 +9,7 @@
 int mr_heightmap_normalize_impl(mr_context* ctx, const uint16_t* in, uint64_t count, float* out);
 int mr_selftest_fastdiv_impl(mr_context* ctx, float b, int force_fast, unsigned long long* mismatches_dev);
 int mr_polygon_offsets_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t* first_tri_dev);
+int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]);
 int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t seed,
                                uint64_t poly_index0, uint32_t* out_dev);
 int mr_synth_heightmap_u16_impl(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t row0, uint32_t rows,
@@ -452,6 +453,12 @@ int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job) {
     if (sn) { rc = mr_copy_back(ctx, j.ntri_out, d.ntri_out, (size_t)j.npoly * 4); if (rc) return rc; }
     if (sv || sb || ss || sn) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MR_OK;
+}
+
+int mr_triangulate_tier_counts(mr_context* ctx, uint32_t out[8]) {
+    if (!ctx || !out) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    return mr_triangulate_tier_counts_impl(ctx, out);
 }
 
 uint64_t mr_rng_state0(uint64_t seed, uint64_t index) { return mr_rng_state0_hd(seed, index); }

@@ -1240,6 +1240,18 @@ int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev,
     return MR_OK;
 }
 
+int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]) {
+    memset(out, 0, 8 * sizeof(uint32_t));
+    if (!ctx->scratch[SLOT_WORK]) return MR_OK;
+    uint32_t hdr[64];
+    MR_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->scratch[SLOT_WORK], sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream));
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < NUM_CLASSES; ++c) out[c] = hdr[32 + c];  // spec_count
+    out[6] = hdr[40];                                              // general_count
+    out[7] = hdr[8 + NUM_CLASSES - 1] - hdr[NUM_CLASSES - 1];      // class_end - class_begin of the last class
+    return MR_OK;
+}
+
 int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     // all pointers in *j are device pointers here (staging happened in api.cu)
     const uint32_t npoly = j->npoly;

@@ -57,7 +57,9 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
         }
         // conflict lists pay for themselves on larger polygons only (measured: 1.35-1.55x for n up to 1024,
         // a small loss for n <= 64 where the per-edge polling overhead exceeds the search it saves)
-        k.item_cap = c >= 1 ? 6u * k.nmax + 64u : 0u;  // 6 B per item >= the 16 B per add that reuse the pool later
+        // items are not recycled, so the pool must hold every item ever created (n initial + one per straddled
+        // point node met by a pending edge): ~3-4n on convex input; 4n+64 sent half of the 1024-gons to the retry tier
+        k.item_cap = c >= 1 ? 6u * k.nmax + 64u : 0u;  // the pool is reused by the mountain-phase arrays later
     } else {
         k.item_cap = 0;  // measured: conflict lists slow the retry tier down (8.1 vs 6.1 ms on the 100k star batch)
         k.node_cap = MR_NODE_CAP(k.nmax);
@@ -82,7 +84,8 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     L.stack = o;   o += align16((size_t)k.stack_cap * 2);
     L.nodes = o;   o += align16((size_t)k.node_cap * 8);
     L.crumb = o;   o += align16((size_t)k.node_cap * 2);
-    // mountain-phase arrays; in the items tier they reuse the item pool (dead once part 1 is done)
+    // mountain-phase arrays reuse what is dead once part 1 is done: the item pool (with the per-edge
+    // tables) and, for efirst, the point-location cache
     const size_t pool = o;
     L.add_pp = o;  o += align16((size_t)k.add_cap * 4);
     L.add_key = o; o += align16((size_t)k.add_cap * 4);
@@ -96,12 +99,12 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
         L.it_node = o; o += align16((size_t)k.item_cap * 2);
         L.it_next = o; o += align16((size_t)k.item_cap * 2);
         L.it_edge = o; o += align16((size_t)k.item_cap * 2);
-        if (o < mountain_end) o = mountain_end;
         L.ehead = o;   o += align16((size_t)k.nmax * 2);
         L.eul = o;     o += align16((size_t)k.nmax * 4);
         L.ctr = o;     o += 16;
+        if (o < mountain_end) o = mountain_end;
     }
-    L.efirst = o;  o += align16((size_t)k.nmax * 2);
+    L.efirst = L.loc;
     L.total = o;
     return L;
 }

@@ -24,6 +24,8 @@ for tune in ("0x1001", "0x1000", "0x1004", "0x1008"):
     os.environ["MR_TUNE"] = tune
     b = P.create_polygons(xy, fp, seed=5); ctx.sync()
     ok = int((b.status == 0).sum().item())
+    import ctypes as C
+    tc = (C.c_uint32 * 8)(); ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc); print("tier counts", list(tc))
     ts = []
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
