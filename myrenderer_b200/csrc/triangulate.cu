@@ -18,7 +18,6 @@
 // checked per triangle with a musl-exact atan2f; if any check fails the polygon falls back to a
 // literal restatement of the loop.
 #include <algorithm>
-#include <cstdlib>
 #include "common.cuh"
 #include "unirand.cuh"
 
@@ -45,15 +44,6 @@ struct Caps {
     uint32_t add_cap;    // mountain adds
 };
 
-__host__ __device__ inline Caps tier0_caps(int c) {
-    Caps k;
-    k.nmax = class_nmax(c);
-    k.node_cap = 6u * k.nmax + 32u;
-    k.stack_cap = 2u * k.nmax + 32u;
-    k.add_cap = 2u * k.nmax + 16u;
-    // sorted lists alias the node arena: 2*add_cap entries * 14 bytes must fit in 12*node_cap
-    return k;
-}
 __host__ __device__ inline Caps tier1_caps(uint32_t nmax) {
     Caps k;
     k.nmax = nmax;
@@ -105,7 +95,6 @@ struct BatchArgs {
     uint32_t* ntri_out;
     uint32_t stride, off_x, off_c;  // off_c == 0xFFFFFFFF: no colour attribute
     int fast32;                     // stride 32, offsets {0,16} in either order, 32B-aligned base
-    uint32_t tune;                  // experiment knobs (MR_TUNE), see triangulate_fast.cuh
     // work lists
     const uint32_t* order;        // polygon ids grouped by class
     const uint32_t* class_begin;  // NUM_CLASSES: first position of the class in `order` (sorted by size, descending)
@@ -1305,10 +1294,6 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                 reinterpret_cast<uintptr_t>(a.vtx_out) % 32 == 0)
                    ? 1
                    : 0;
-    {
-        const char* t = getenv("MR_TUNE");
-        a.tune = t ? (uint32_t)strtoul(t, nullptr, 0) : 0u;
-    }
     a.order = order;
     a.class_begin = class_begin;
     a.class_end = class_end;

@@ -435,8 +435,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     __syncwarp();
 
     // ---- conflict lists of the pending edges (items tier) ---------------------------------------------
-    const bool use_items = caps.item_cap != 0 && !(a.tune & 1u);
-    const uint32_t item_period = (((a.tune >> 1) & 15u) ? ((a.tune >> 1) & 15u) : 4u) * ((n + 63u) / 64u);
+    const bool use_items = caps.item_cap != 0;
+    const uint32_t item_period = 4u * ((n + 63u) / 64u);  // measured best of 1/2/4/8 on n <= 1024
     uint16_t* it_node = reinterpret_cast<uint16_t*>(ws + L.it_node);
     uint16_t* it_next = reinterpret_cast<uint16_t*>(ws + L.it_next);
     uint16_t* it_edge = reinterpret_cast<uint16_t*>(ws + L.it_edge);
@@ -570,7 +570,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             ok = P.search_from_root(up, lo);
             if (!ok) break;
         }
-        ok = P.pass2(p1, up, lo, lane, ((a.tune >> 8) & 31u) ? ((a.tune >> 8) & 31u) : 16u);  // pass 2
+        ok = P.pass2(p1, up, lo, lane, 16u);  // pass 2: scan as written below 16 entries, REDUX arg-min above
         __syncwarp();
     }
     if (P.requeue) return F_REQUEUE_SPEC;

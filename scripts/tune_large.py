@@ -1,4 +1,4 @@
-"""Experiment: polygon kernel knobs on large polygons (convex ellipses, sizes log-uniform 8..1024)."""
+"""Timing of the polygon kernel on large polygons (convex ellipses; `log`: sizes log-uniform 8..1024, `big`: 512..1024)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -20,8 +20,7 @@ npoly = 20000
 fp = O.synth_polygon_sizes(0x5EED0005, npoly, 8, 1024, 1) if which == "log" else O.synth_polygon_sizes(1, npoly, 512, 1024, 0)
 xy = ellipses(fp, 3)
 ctx = mr.Context(0); P = mr.Polygon(ctx)
-for tune in ("0x1001", "0x1000", "0x1004", "0x1008"):
-    os.environ["MR_TUNE"] = tune
+for tune in ("default",):
     b = P.create_polygons(xy, fp, seed=5); ctx.sync()
     ok = int((b.status == 0).sum().item())
     import ctypes as C
