@@ -56,23 +56,9 @@ def test_terrain_16384_properties_and_sampled_bands(ctx, oracle):
 
 
 def _ellipse_batch(first_point, seed):
-    """Convex polygons (the family the reference algorithm triangulates correctly at every size),
-    generated on the GPU in float64: vertex k at angle 2*pi*(k + jitter)/n on a rotated ellipse."""
-    import torch
+    from myrenderer_b200.workloads import ellipse_batch
 
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    fp = torch.from_numpy(first_point.astype(np.int64)).cuda()
-    nper = fp[1:] - fp[:-1]
-    npoly, tot = len(nper), int(fp[-1])
-    pid = torch.repeat_interleave(torch.arange(npoly, device="cuda"), nper)
-    k = torch.arange(tot, device="cuda") - fp[:-1][pid]
-    th = 2 * np.pi * (k.double() + 0.8 * torch.rand(tot, generator=g, device="cuda", dtype=torch.float64) - 0.4) / nper[pid].double()
-    a = (40 + 50 * torch.rand(npoly, generator=g, device="cuda", dtype=torch.float64))[pid]
-    b = (40 + 50 * torch.rand(npoly, generator=g, device="cuda", dtype=torch.float64))[pid]
-    ph = (6.28 * torch.rand(npoly, generator=g, device="cuda", dtype=torch.float64))[pid]
-    x, y = a * torch.cos(th), b * torch.sin(th)
-    xy = torch.stack([100 + torch.cos(ph) * x - torch.sin(ph) * y, 100 + torch.sin(ph) * x + torch.cos(ph) * y], 1)
-    return xy.float().contiguous(), pid
+    return ellipse_batch(first_point, seed)
 
 
 def test_polygons_1m_skewed_sizes(ctx, oracle):
