@@ -2,7 +2,7 @@
 //
 // Replaces the body of Terrain.create_terrain (Terrain/Terrain.zig:88-129) plus the per-frame WGSL
 // vertex formula (Terrain/Terrain.zig:21-50) with a one-off mesh build:
-//   terrain_vertices_k   streaming stencil.  A (16+2) x (256+2) height tile is staged in shared memory
+//   terrain_vertices_k   streaming stencil.  A (8+2) x (256+2) height tile is staged in shared memory
 //                        as f32 (the u16 -> f32 of Terrain.zig:120 fused into the load), then one
 //                        thread per column walks down the tile with a rolling 3-row window and emits
 //                        ONE 32-byte store (STG.E.ENL2.256: position slot + normal slot) per vertex,
@@ -24,7 +24,13 @@
 namespace {
 
 constexpr int TV_THREADS = 256;  // columns per tile
-constexpr int TV_ROWS = 16;      // rows per tile
+#ifndef MR_TV_ROWS
+#define MR_TV_ROWS 8  // measured: 8 beats 4, 16 and 32 at n = 4096 and n = 16384
+#endif
+#ifndef MR_TV_STORE
+#define MR_TV_STORE 0  // 0: default policy, 1: evict-first (.cs), 2: L1 no-allocate
+#endif
+constexpr int TV_ROWS = MR_TV_ROWS;  // rows per tile
 
 struct DivConst {
     float b;  // divisor
@@ -73,7 +79,13 @@ __device__ __forceinline__ float load_height(const void* base, size_t idx) {
 __device__ __forceinline__ void store_vertex32(unsigned char* p, float a0, float a1, float a2, float b0,
                                                float b1, float b2) {
     // one 256-bit store: [a0 a1 a2 0 | b0 b1 b2 0]
+#if MR_TV_STORE == 1
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2),
+#elif MR_TV_STORE == 2
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2),
+#else
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2),
+#endif
                  "f"(0.0f), "f"(b0), "f"(b1), "f"(b2), "f"(0.0f)
                  : "memory");
 }
