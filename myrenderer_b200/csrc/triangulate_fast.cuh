@@ -6,8 +6,9 @@
 //     point_is_above(a, b) (Triangulation.zig:128-136) is the integer compare a < b on values that
 //     are already in registers; coordinates are only loaded for is_left_of.  Original ids come
 //     back at emission (the emit order of :405-422 is defined on original ids).
-//   * 8-byte nodes: {child1:16 | child2:16, pa:14 | type:2 | pb:16} fetched with one LDS.64;
-//     the crumb of segment nodes lives in a side array (read only by the mountain scan); the
+//   * 8-byte nodes: {child1:16 | child2:16, pa:13 | crumb-is-right:1 | type:2 | pb:16} fetched with one
+//     LDS.64.  A segment node's crumb is always one of its two children (:351-358), so one bit holds
+//     it; point and trapezoid nodes always have a null crumb.  The
 //     breadcrumb chain of the segment search (:253-257,:306-310) is an explicit stack -- the
 //     reference restores every crumb to null before the search returns, so this is unobservable.
 //   * no null checks on inner nodes: point and segment nodes always have both children and their
@@ -31,7 +32,8 @@
 //     O(k) scan of :329-337: same winner, because ties go to the lowest stack index in both.
 #pragma once
 
-constexpr uint32_t FNIL14 = 0x3FFFu;  // null in the 14-bit pa field
+constexpr uint32_t FNIL14 = 0x1FFFu;  // null in the 13-bit pa field (ranks are < 1024 on this path)
+constexpr uint32_t CRUMB_RIGHT = 0x2000u;  // segment node: crumb == child2 (the inside is on the right)
 constexpr uint32_t FNIL = 0xFFFFu;
 
 struct FCaps {
@@ -64,13 +66,13 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
         k.item_cap = 0;  // measured: conflict lists slow the retry tier down (8.1 vs 6.1 ms on the 100k star batch)
         k.node_cap = MR_NODE_CAP(k.nmax);
         k.stack_cap = MR_STACK_CAP(k.nmax);
-        k.add_cap = 4u * k.nmax + 32u;  // sort arrays (20 B per add) alias the node arena (10 B per node)
+        k.add_cap = 3u * k.nmax + 16u;  // sort arrays (20 B per add) alias the node arena (8 B per node)
     }
     return k;
 }
 
 struct FLayout {
-    size_t sxy, orig, rk, loc, cstack, stack, nodes, crumb, add_pp, add_key, add_m, mcount, mstart, efirst, total;
+    size_t sxy, orig, rk, loc, cstack, stack, nodes, add_pp, add_key, add_m, mcount, mstart, efirst, total;
     size_t it_node, it_next, it_edge, ehead, eul, ctr;  // items tier only
 };
 __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
@@ -80,10 +82,9 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     L.orig = o;    o += align16((size_t)k.nmax * 2);
     L.rk = o;      o += align16((size_t)k.nmax * 2);
     L.loc = o;     o += align16((size_t)k.nmax * 2);
-    L.cstack = o;  o += align16((size_t)k.nmax * 2);
+    L.cstack = o;  o += k.item_cap ? 0 : align16((size_t)k.nmax * 2);  // only the search from the root uses it
     L.stack = o;   o += align16((size_t)k.stack_cap * 2);
     L.nodes = o;   o += align16((size_t)k.node_cap * 8);
-    L.crumb = o;   o += align16((size_t)k.node_cap * 2);
     // mountain-phase arrays reuse what is dead once part 1 is done: the item pool (with the per-edge
     // tables) and, for efirst, the point-location cache
     const size_t pool = o;
@@ -115,7 +116,6 @@ enum : int { F_DONE = 0, F_REQUEUE_SPEC = 1, F_REQUEUE_GENERAL = 2 };
 struct FPoly {
     const float2* sxy;
     uint2* nd;
-    uint16_t* crumb;
     uint16_t* stack;
     uint16_t* cstack;
     uint32_t nnodes, nstack, status;
@@ -165,11 +165,7 @@ struct FPoly {
         if (lower == FNIL || upper == FNIL) return false;
         nd[lower] = make_uint2(v.x, (v.y & 0xFFFFC000u) | pid);        // point1 = pid
         nd[upper] = make_uint2(v.x, (v.y & 0x0000FFFFu) | (pid << 16));  // point2 = pid
-        const uint16_t cb = crumb[base];
-        crumb[lower] = cb;
-        crumb[upper] = cb;
         nd[base] = make_uint2(upper | (lower << 16), pid | (T_POINT << 14) | (FNIL << 16));
-        crumb[base] = (uint16_t)FNIL;
         return true;
     }
 
@@ -287,8 +283,7 @@ struct FPoly {
             lx = (lx & 0xFFFF0000u) | (bch & 0xFFFFu);
             rx = (rx & 0x0000FFFFu) | (bch & 0xFFFF0000u);
             __syncwarp();
-            nd[base_id] = make_uint2(left | (right << 16), up | (T_SEGMENT << 14) | (lo << 16));
-            crumb[base_id] = (uint16_t)(crumb_left ? left : right);
+            nd[base_id] = make_uint2(left | (right << 16), up | (crumb_left ? 0u : CRUMB_RIGHT) | (T_SEGMENT << 14) | (lo << 16));
             if (lo == low) {  // :366-373
                 lx = (lx & 0xFFFFu) | (base_id << 16);
                 ly = (ly & 0xFFFFu) | (low << 16);
@@ -299,7 +294,6 @@ struct FPoly {
                 lx = (lx & 0xFFFFu) | (base_id << 16);
                 ly = (ly & 0xFFFFu) | (low << 16);
                 nd[left] = make_uint2(lx, ly);
-                crumb[left] = (uint16_t)FNIL;
                 left = alloc();
                 if (left == FNIL) return false;
                 lx = fresh;
@@ -308,7 +302,6 @@ struct FPoly {
                 rx = (rx & 0xFFFF0000u) | base_id;
                 ry = (ry & 0xFFFFu) | (low << 16);
                 nd[right] = make_uint2(rx, ry);
-                crumb[right] = (uint16_t)FNIL;
                 right = alloc();
                 if (right == FNIL) return false;
                 rx = fresh;
@@ -319,9 +312,7 @@ struct FPoly {
             __syncwarp();
         }
         nd[left] = make_uint2(lx, ly);
-        crumb[left] = (uint16_t)FNIL;
         nd[right] = make_uint2(rx, ry);
-        crumb[right] = (uint16_t)FNIL;
         return true;
     }
 };
@@ -393,7 +384,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         uint32_t n2 = 32;
         while (n2 < n) n2 <<= 1;
         unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + L.nodes) + n;  // 8n + 8*n2 <= 8*node_cap
-        uint16_t* kidx = reinterpret_cast<uint16_t*>(ws + L.crumb);                         // 2*n2 <= 2*node_cap
+        uint16_t* kidx = reinterpret_cast<uint16_t*>(ws + L.add_pp);                        // 2*n2 <= 4n <= 4*add_cap
         for (uint32_t i = lane; i < n2; i += 32) {
             unsigned long long k = ~0ull;  // padding sorts last
             if (i < n) {
@@ -454,7 +445,6 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     FPoly P;
     P.sxy = sxy;
     P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
-    P.crumb = reinterpret_cast<uint16_t*>(ws + L.crumb);
     P.stack = reinterpret_cast<uint16_t*>(ws + L.stack);
     P.cstack = reinterpret_cast<uint16_t*>(ws + L.cstack);
     P.nnodes = 1;  // :479 root trapezoid
@@ -466,7 +456,6 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     P.tier_stack_cap = caps.stack_cap;
     P.requeue = false;
     P.nd[0] = make_uint2(FNIL | (FNIL << 16), FNIL14 | (T_TRAPEZOID << 14) | (FNIL << 16));
-    P.crumb[0] = (uint16_t)FNIL;
     __syncwarp();
 
     // ---- conflict lists of the pending edges (items tier) ---------------------------------------------
@@ -622,7 +611,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     uint32_t* mcount = reinterpret_cast<uint32_t*>(ws + L.mcount);
     uint16_t* mstart = reinterpret_cast<uint16_t*>(ws + L.mstart);
     uint16_t* efirst = reinterpret_cast<uint16_t*>(ws + L.efirst);
-    const uint32_t PMASK = 0xFFFF3FFFu;  // (pa, pb) without the type bits
+    const uint32_t PMASK = 0xFFFF1FFFu;  // (pa, pb) without the type and crumb bits
 
     uint32_t A = 0;
     bool bad = false, over = false;
@@ -635,7 +624,11 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             if (FPoly::type_of(v.y) == T_TRAPEZOID) {
                 const uint32_t c1 = v.x & 0xFFFFu, c2 = v.x >> 16;
                 if (c1 != FNIL) {                                    // :516
-                    if (P.crumb[c1] == (P.nd[c1].x >> 16)) {         // :517 crumb == child2
+                    // :517 crumb == child2.  Segment node: the stored bit; any other node has a null crumb,
+                    // which equals child2 only when child2 is null too.
+                    const uint2 c1n = P.nd[c1];
+                    const bool inside = FPoly::type_of(c1n.y) == T_SEGMENT ? (c1n.y & CRUMB_RIGHT) != 0u : (c1n.x >> 16) == FNIL;
+                    if (inside) {
                         mypp = v.y & PMASK;
                         if ((mypp & FNIL14) == FNIL14 || (mypp >> 16) == FNIL || c2 == FNIL) {
                             lane_bad = true;  // :524-527
