@@ -39,18 +39,20 @@ constexpr uint32_t FNIL = 0xFFFFu;
 struct FCaps {
     uint32_t nmax, node_cap, stack_cap, add_cap;
     uint32_t item_cap;  // 0: no conflict lists (the segment search runs from the root at insertion)
+    bool par_separate_out;  // parallel search writes its list straight into node_stack (retry tier)
 };
 // tight: sized for the typical polygon of the class; spec: the contract caps (second chance in shared memory)
 __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
     FCaps k;
     k.nmax = class_nmax(c);
+    k.par_separate_out = spec;
     if (!spec) {
         if (c == 0) {
             // tier 0 is register-limited to 5 blocks/SM, which leaves ~11 KB of shared memory per warp:
             // spend it on contract-cap node arenas and a deep stack so that almost no polygon needs the
             // retry tier (whose separate launch is tail-bound)
             k.node_cap = MR_NODE_CAP(k.nmax);
-            k.stack_cap = 4u * k.nmax + 64u;
+            k.stack_cap = 64u;  // the serial search hands over to the parallel one at 48 leaves (own output list)
             k.add_cap = 3u * k.nmax + 32u;
         } else {
             k.node_cap = 6u * k.nmax + 16u;
@@ -93,6 +95,10 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     L.add_m = o;   o += align16((size_t)k.add_cap * 2);
     L.mcount = o;  o += align16((size_t)k.add_cap * 4);
     L.mstart = o;  o += align16((size_t)(k.add_cap + 1) * 2);
+    if (k.par_separate_out) {  // retry tier: room for the parallel search's items up to the contract stack cap
+        const size_t need = pool + 16 + align16((size_t)(k.stack_cap + 2u) * 4);
+        if (o < need) o = need;
+    }
     const size_t mountain_end = o;
     L.it_node = L.it_next = L.it_edge = L.ehead = L.eul = L.ctr = 0;
     if (k.item_cap) {
@@ -212,8 +218,9 @@ struct FPoly {
         return first ? (v.x & 0xFFFFu) : (v.x >> 16);
     }
 
-    // pass 1 of add_segment (:230-314), literally from the root
-    __device__ bool search_from_root(uint32_t up, uint32_t lo) {
+    // pass 1 of add_segment (:230-314), literally from the root.  Returns 1 when done, 0 on failure, and 2 when
+    // the walk has produced `give_up` leaves without finishing (the caller then redoes it in parallel).
+    __device__ int search_from_root(uint32_t up, uint32_t lo, uint32_t give_up) {
         const float2 Pu = sxy[up], Pl = sxy[lo];
         uint32_t base = 0, ncr = 0;
         nstack = 0;
@@ -226,11 +233,84 @@ struct FPoly {
                 if (both) cstack[ncr++] = (uint16_t)base;
                 base = next;
             }
-            if (!push(base)) return false;  // :302
-            if (ncr == 0) break;            // :306-313
+            if (!push(base)) return 0;  // :302
+            if (ncr == 0) break;        // :306-313
+            if (nstack >= give_up) return 2;
             base = nd[cstack[--ncr]].x >> 16;
         }
-        return true;
+        return 1;
+    }
+
+    // The same search as a lane-parallel frontier expansion, for the searches that explode (the same
+    // trapezoid reached over many DAG paths is pushed once per path).  Every branch of the walk is an
+    // item in a linked list; a straddled point node links a sibling item right behind the current one,
+    // so the list order is the order in which the serial walk pushes its leaves.  All lanes advance all
+    // items until every item sits on a trapezoid; the list is then copied into node_stack.
+    //   it_node/it_next: item arrays (cap entries), out: node_stack to fill (out_cap entries), ctr: shared
+    //   word.  Returns 1 done, 0 failure (status/requeue set).
+    __device__ int search_parallel(uint32_t up, uint32_t lo, uint16_t* it_node, uint16_t* it_next, uint32_t cap,
+                                   uint16_t* out, uint32_t out_cap, uint32_t* ctr, uint32_t lane) {
+        const float2 Pu = sxy[up], Pl = sxy[lo];
+        __syncwarp();
+        if (lane == 0) {
+            it_node[0] = 0;
+            it_next[0] = (uint16_t)FNIL;
+            ctr[0] = 1;
+            ctr[1] = 0;
+        }
+        __syncwarp();
+        for (;;) {
+            const uint32_t cnt = min(ctr[0], cap);
+            bool advanced = false;
+            for (uint32_t it = lane; it < cnt; it += 32) {
+                uint32_t node = it_node[it];
+                uint2 v = nd[node];
+                if (type_of(v.y) == T_TRAPEZOID) continue;
+                advanced = true;
+                do {
+                    bool both;
+                    const uint32_t next = dfs_step(v, up, lo, Pu, Pl, &both);
+                    if (both) {
+                        const uint32_t nw = atomicAdd(&ctr[0], 1u);
+                        if (nw >= cap) {
+                            ctr[1] = 1;
+                            break;
+                        }
+                        it_node[nw] = (uint16_t)(v.x >> 16);  // child2: after everything under child1
+                        it_next[nw] = it_next[it];
+                        it_next[it] = (uint16_t)nw;
+                    }
+                    node = next;
+                    v = nd[node];
+                } while (type_of(v.y) != T_TRAPEZOID);
+                it_node[it] = (uint16_t)node;
+            }
+            __syncwarp();
+            if (ctr[1]) {  // more items than `cap`: at least that many leaves
+                if (cap > spec_stack_cap) status |= MR_POLY_ARENA; else requeue = true;
+                return 0;
+            }
+            if (!__any_sync(0xFFFFFFFFu, advanced) && ctr[0] == cnt) break;
+        }
+        // copy in list order; the contract cap applies to the number of pushes exactly as in the serial walk
+        const uint32_t total = ctr[0];
+        if (total > spec_stack_cap) {
+            status |= MR_POLY_ARENA;
+            return 0;
+        }
+        if (total > out_cap) {
+            requeue = true;
+            return 0;
+        }
+        uint32_t it = 0;
+        for (uint32_t j = 0; j < total; ++j) {  // warp-uniform walk
+            if (lane == 0) out[j] = it_node[it];
+            it = it_next[it];
+        }
+        __syncwarp();
+        stack = out;
+        nstack = total;
+        return 1;
     }
 
     // pass 2 of add_segment (:316-395) on node_stack; p1 is the rank id of the edge's first point
@@ -483,6 +563,28 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     }
     __syncwarp();
 
+    // scratch of the parallel search (tiers without conflict lists): the mountain-phase arrays, free in part 1
+    uint16_t* const stack_home = P.stack;
+    uint16_t *par_node = nullptr, *par_next = nullptr, *par_out = nullptr;
+    uint32_t* par_ctr = nullptr;
+    uint32_t par_cap = 0, par_out_cap = 0;
+    if (!use_items) {
+        const size_t bytes = (L.efirst == L.loc ? L.total : L.efirst) - L.add_pp - 16;  // pool region minus the counter
+        par_ctr = reinterpret_cast<uint32_t*>(ws + L.add_pp);
+        unsigned char* base = ws + L.add_pp + 16;
+        if (caps.par_separate_out) {  // retry tier: the list goes to the (contract-cap) node_stack itself
+            par_cap = (uint32_t)(bytes / 4);
+            par_out = stack_home;
+            par_out_cap = caps.stack_cap;
+        } else {  // typical-case tier: items and the output list share the region 2:1
+            par_cap = (uint32_t)(bytes / 6);
+            par_out = reinterpret_cast<uint16_t*>(base + (size_t)par_cap * 4);
+            par_out_cap = par_cap;
+        }
+        par_node = reinterpret_cast<uint16_t*>(base);
+        par_next = par_node + par_cap;
+    }
+
     const uint32_t refresh_every = (n + 63u) / 64u;
     bool ok = true;
     for (uint32_t at = 0; at < n && ok; ++at) {  // :484-494
@@ -591,7 +693,16 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             ehead[edge] = (uint16_t)FNIL;
             if (!ok) break;
         } else {
-            ok = P.search_from_root(up, lo);
+            // serial walk; a search that has already produced 48 leaves is one of the exploding ones and is
+            // redone as a parallel frontier expansion (items + output list live in the mountain arrays,
+            // unused during part 1)
+            P.stack = stack_home;
+            const int sr = P.search_from_root(up, lo, par_cap ? 48u : 0xFFFFFFFFu);
+            if (sr == 2) {
+                if (!P.search_parallel(up, lo, par_node, par_next, par_cap, par_out, par_out_cap, par_ctr, lane)) ok = false;
+            } else if (sr == 0) {
+                ok = false;
+            }
             if (!ok) break;
         }
         ok = P.pass2(p1, up, lo, lane, 16u);  // pass 2: scan as written below 16 entries, REDUX arg-min above
