@@ -278,6 +278,28 @@ def test_star_polygons_seeded(ctx, oracle):
     assert 0 in seen and any(s & 4 for s in seen) and any(s & 8 for s in seen)
 
 
+def test_fast_path_is_the_one_that_runs(ctx, oracle):
+    """On the benchmark's batch nothing should need the retry tier or the general (global-memory) path:
+    the shared-memory fast path handles every polygon, including the ones whose search explodes."""
+    import ctypes as C
+
+    import myrenderer_b200 as mr
+
+    seed = 0x5EED0003
+    fp = oracle.synth_polygon_sizes(seed, 20000, 8, 64)
+    xy = oracle.synth_polygons(seed, fp)
+    mr.Polygon(ctx).create_polygons(xy, fp, seed=seed)
+    tc = (C.c_uint32 * 8)()
+    ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
+    assert tc[6] == 0 and tc[7] == 0, list(tc)      # general path, >1024 tier
+    assert sum(tc[0:6]) <= 20000 // 100, list(tc)    # retry tier: at most a percent
+    # coincident points force the general path, and it is counted
+    sq = np.array([[0, 0], [10, 0], [10, 0], [10, 10], [0, 10]], dtype=np.float32)
+    mr.Polygon(ctx).create_polygons(sq, np.array([0, 5], dtype=np.uint64), seed=1)
+    ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
+    assert tc[6] == 1
+
+
 def test_zigauto_layout_and_index_offset(ctx, oracle):
     seed = 99
     fp = oracle.synth_polygon_sizes(seed, 300, 3, 40)
