@@ -482,17 +482,17 @@ __device__ __forceinline__ void triangle_order(uint32_t point, uint32_t axis1, u
     }
 }
 
-// Polygon.zig:50-57,66-71: palette[(len/3)%4], channels (hex&0xff, hex>>8&0xff, hex>>16&0xff)/255
+// Polygon.zig:50-57,66-71: palette[(len/3)%4], channels (hex&0xff, hex>>8&0xff, hex>>16&0xff)/255.0 of
+// 0x5e315b, 0xcfff70, 0x3ca370, 0x4b5bab.  The twelve quotients are constants; their bit patterns
+// (IEEE f32 division) are the ones of SURVEY 8-a12 and are checked against the oracle's computed
+// palette in tests/test_oracle_cpu.py::test_palette_bits and by every vertex-buffer comparison.
 __device__ __forceinline__ float3 palette(uint32_t tri) {
-    uint32_t hex;
     switch (tri & 3u) {
-        case 0: hex = 0x5e315bu; break;
-        case 1: hex = 0xcfff70u; break;
-        case 2: hex = 0x3ca370u; break;
-        default: hex = 0x4b5babu; break;
+        case 0: return make_float3(__uint_as_float(0x3EB6B6B7u), __uint_as_float(0x3E44C4C5u), __uint_as_float(0x3EBCBCBDu));
+        case 1: return make_float3(__uint_as_float(0x3EE0E0E1u), __uint_as_float(0x3F800000u), __uint_as_float(0x3F4FCFD0u));
+        case 2: return make_float3(__uint_as_float(0x3EE0E0E1u), __uint_as_float(0x3F23A3A4u), __uint_as_float(0x3E70F0F1u));
+        default: return make_float3(__uint_as_float(0x3F2BABACu), __uint_as_float(0x3EB6B6B7u), __uint_as_float(0x3E969697u));
     }
-    return make_float3(__fdiv_rn((float)(hex & 0xffu), 255.0f), __fdiv_rn((float)((hex >> 8) & 0xffu), 255.0f),
-                       __fdiv_rn((float)((hex >> 16) & 0xffu), 255.0f));
 }
 
 struct Sink {

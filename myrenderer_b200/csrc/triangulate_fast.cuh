@@ -586,6 +586,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     }
 
     const uint32_t refresh_every = (n + 63u) / 64u;
+    const bool ur_simple = ur_offset < n && ur_prime < n;
+    uint32_t ur_edge = ur_offset;
     bool ok = true;
     for (uint32_t at = 0; at < n && ok; ++at) {  // :484-494
         if (at % refresh_every == 0) {
@@ -638,7 +640,16 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             }
             __syncwarp();
         }
-        const uint32_t edge = (uint32_t)(at * ur_prime + ur_offset) % n;
+        // unirand.zig:16: (at * prime + offset) % top in u32 arithmetic.  With offset, prime < n (always so for
+        // unirand_seed's own output) the sequence is an add-and-wrap; explicit pairs outside that keep the formula.
+        uint32_t edge;
+        if (ur_simple) {
+            edge = ur_edge;
+            ur_edge += ur_prime;
+            if (ur_edge >= n) ur_edge -= n;
+        } else {
+            edge = (uint32_t)(at * ur_prime + ur_offset) % n;
+        }
         const uint32_t p1 = rk[edge];
         const uint32_t p2 = rk[edge + 1u == n ? 0u : edge + 1u];
         const uint32_t up = min(p1, p2), lo = max(p1, p2);  // :218-224 in rank space
