@@ -307,6 +307,36 @@ def test_zigauto_layout_and_index_offset(ctx, oracle):
     _check_batch(ctx, oracle, xy, fp, seed=seed, poly_index0=12345, order="zigauto")
 
 
+def test_generic_vertex_layout_and_odd_unirand_pairs(ctx, oracle):
+    """A vertex layout that is not the 32-byte fast case (stride 40, x at 4, colour at 20), and explicit
+    (offset, prime) pairs outside what unirand_seed produces: offset >= n, prime >= n, prime == 0, and
+    values whose product wraps u32 (unirand.zig:16 is u32 arithmetic) -- same formula in oracle and kernel."""
+    import myrenderer_b200 as mr
+
+    rng = np.random.default_rng(11)
+    sizes = rng.integers(3, 40, 60)
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    pts = []
+    for n in sizes:
+        th = 2 * np.pi * (np.arange(n) + 0.8 * rng.random(n) - 0.4) / n
+        pts.append(np.stack([100 + 60 * np.cos(th), 100 + 45 * np.sin(th)], 1))
+    xy = np.concatenate(pts).astype(np.float32)
+    op = np.zeros((60, 2), dtype=np.uint32)
+    op[:, 0] = rng.integers(0, 100, 60)
+    op[:, 1] = rng.integers(0, 100, 60)
+    op[0] = (0, 0)
+    op[1] = (5, 0)
+    op[2] = (0xFFFFFFF0, 0xFFFFFFF1)
+    op[3] = (123456789, 987654321)
+    lay = mr.VertexLayout(40, ((4, 2), (20, 3)))
+    b = mr.Polygon(ctx, lay).create_polygons(xy, fp, offset_prime=op)
+    ctx.sync()
+    ref = oracle.polygon_batch(xy, fp, offset_prime=op, layout=(40, ((4, 2), (20, 3))), nthreads=0)
+    assert np.array_equal(b.status.cpu().numpy().view(np.uint32), ref["status"])
+    assert np.array_equal(b.vertex_buffer.cpu().numpy(), ref["vtx"])
+    assert np.array_equal(b.bbox.cpu().numpy().view(np.uint32), ref["bbox"].view(np.uint32))
+
+
 def test_convex_and_large_polygons(ctx, oracle):
     """Sizes up to 1024 (every shared-memory class) and 1025..4096 (global-memory tier)."""
     rng = np.random.default_rng(5)
