@@ -61,6 +61,19 @@ inline bool mr_is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Pinned (page-locked) host memory is reachable from kernels under UVA: returns its device alias, or
+// nullptr when `p` is not pinned host memory.  Used for outputs that are produced over a long kernel,
+// where storing straight over PCIe overlaps the transfer with the compute.
+inline void* mr_pinned_device_alias(void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 inline int mr_scratch(mr_context* ctx, int slot, size_t bytes, void** out) {
     if (bytes == 0) bytes = 16;
     if (ctx->scratch_bytes[slot] < bytes) {

@@ -419,6 +419,25 @@ def test_polygon_host_pointers_and_subrange(ctx, oracle):
     assert np.array_equal(vtx, ref["vtx"]) and np.array_equal(bbox.view(np.uint32), ref["bbox"].view(np.uint32))
 
 
+def test_polygon_pinned_host_output_zero_copy(ctx, oracle):
+    """Pinned host vertex buffers are written by the kernels directly (zero-copy over PCIe); pageable
+    ones are staged.  Both must give the oracle's bytes."""
+    import myrenderer_b200 as mr
+
+    torch = _torch()
+    seed = 33
+    fp = oracle.synth_polygon_sizes(seed, 3000, 8, 64)
+    xy = oracle.synth_polygons(seed, fp)
+    ref = oracle.polygon_batch(xy, fp, seed=seed, nthreads=0)
+    ft = ref["first_tri"]
+    P = mr.Polygon(ctx)
+    pinned = torch.full((int(ft[-1]) * 96,), 0xAB, dtype=torch.uint8).pin_memory()
+    status = np.zeros(3000, dtype=np.uint32)
+    P.triangulate(P.job(xy, fp, 3000, vtx_out=pinned, first_tri=ft, status_out=status, seed=seed))
+    assert np.array_equal(status, ref["status"])
+    assert np.array_equal(pinned.numpy(), ref["vtx"])
+
+
 def test_unirand_device_port(ctx, oracle):
     torch = _torch()
     tops = np.concatenate([np.arange(2, 300), [509, 521, 1013, 1024, 1723, 1724, 4096]])
