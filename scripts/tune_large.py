@@ -16,7 +16,7 @@ def ellipses(fp, seed):
     return np.stack([100+np.cos(ph)*x-np.sin(ph)*y, 100+np.sin(ph)*x+np.cos(ph)*y], 1).astype(np.float32)
 
 which = sys.argv[1] if len(sys.argv) > 1 else "log"
-npoly = 20000
+npoly = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 fp = O.synth_polygon_sizes(0x5EED0005, npoly, 8, 1024, 1) if which == "log" else O.synth_polygon_sizes(1, npoly, 512, 1024, 0)
 xy = ellipses(fp, 3)
 ctx = mr.Context(0); P = mr.Polygon(ctx)
