@@ -30,6 +30,8 @@ constexpr int NBINS = MR_MAX_POLYGON_POINTS + 1;  // polygons are queued by exac
 constexpr int MAX_WARPS_PER_BLOCK = 4;
 
 __host__ __device__ inline uint32_t class_nmax(int c) { return 64u << c; }
+// warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
+inline int team_warps(int c) { return c >= 3 ? 4 : (c == 2 ? 2 : 1); }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
     while (c < NUM_CLASSES - 1 && n > class_nmax(c)) ++c;
@@ -1038,7 +1040,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
         if (idx >= count) break;
         const uint32_t pi = list[begin + idx];
         Result r;
-        int rc = process_polygon_fast(a, pi, ws, caps, L, &r);
+        int rc = process_polygon_fast<1>(a, pi, ws, caps, L, &r, nullptr);
         if (rc == F_REQUEUE_SPEC && spec) rc = F_REQUEUE_GENERAL;  // the spec tier has no bigger shared-memory tier
         if (rc == F_DONE) {
             write_result(a, pi, r);
@@ -1049,6 +1051,43 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
                 a.general_list[atomicAdd(a.general_count, 1u)] = pi;
         }
         __syncwarp();
+    }
+}
+
+// Fast path for the large classes: one polygon per block, W warps per polygon (see "warp teams" in
+// triangulate_fast.cuh).  Typical-case arenas only; overflow goes to the spec tier of triangulate_fast_k.
+template <int W>
+__global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, int c) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t tcmd[4];  // [0] command, [1] n, [2] item count at refresh start, [3] queue index
+    const FCaps caps = fast_caps(c, false);
+    const FLayout L = fast_layout(caps);
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool main_warp = threadIdx.x < 32u;
+    const uint32_t begin = a.class_begin[c];
+    const uint32_t count = a.class_end[c] - begin;
+    for (;;) {
+        if (threadIdx.x == 0) tcmd[3] = atomicAdd(&a.queue_head[c], 1u);
+        __syncthreads();
+        const uint32_t idx = tcmd[3];
+        if (idx >= count) break;
+        if (main_warp) {
+            const uint32_t pi = a.order[begin + idx];
+            Result r;
+            const int rc = process_polygon_fast<W>(a, pi, smem, caps, L, &r, tcmd);
+            if (lane == 0) tcmd[0] = TEAM_STOP;
+            team_bar<W>();
+            if (rc == F_DONE) {
+                write_result(a, pi, r);
+            } else if (lane == 0) {
+                if (rc == F_REQUEUE_SPEC)
+                    a.spec_list[begin + atomicAdd(&a.spec_count[c], 1u)] = pi;
+                else
+                    a.general_list[atomicAdd(a.general_count, 1u)] = pi;
+            }
+        } else {
+            team_helper<W>(smem, caps, L, tcmd);
+        }
     }
 }
 
@@ -1310,6 +1349,19 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
         for (int c = 0; c < NUM_CLASSES - 1; ++c) {
             const FCaps caps = fast_caps(c, spec != 0);
             const FLayout L = fast_layout(caps);
+            const int team = spec ? 1 : team_warps(c);
+            if (team > 1) {  // one polygon per block, `team` warps per polygon
+                const size_t smem = L.total;
+                if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
+                auto kern = team == 2 ? triangulate_team_k<2> : triangulate_team_k<4>;
+                MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));
+                if (per_sm < 1) per_sm = 1;
+                kern<<<(unsigned)(ctx->sm_count * per_sm), team * 32, smem, ctx->stream>>>(a, c);
+                MR_LAUNCH_CHECK(ctx, "triangulate_team_k");
+                continue;
+            }
             int wpb = MAX_WARPS_PER_BLOCK;
             while (wpb > 1 && L.total * wpb > ctx->smem_optin / 2) wpb >>= 1;  // keep >= 2 blocks per SM when possible
             const size_t smem = L.total * wpb;

@@ -397,9 +397,121 @@ struct FPoly {
     }
 };
 
-// All 32 lanes call this.  Returns F_DONE with *res filled, or a requeue code.
+// ---- warp teams (large classes) ----------------------------------------------------------------------
+// In the classes above 128 points a polygon's workspace is so large that only a few polygons fit an SM, and
+// a lone warp issues one instruction every ~6 cycles: most issue slots of the SM sit idle.  There a block of
+// W warps works on ONE polygon: warp 0 (the main warp) runs the algorithm, the other warps join it for the
+// lane-parallel phases -- the refresh of the point-location caches and of the pending edges' conflict lists --
+// which are loops over independent entries.  Protocol (all block-wide barriers, same count on every warp):
+//   main: tcmd[0] = TEAM_REFRESH|flags; barrier; its share of the refresh; barrier         (per refresh)
+// ("barrier" = named barrier 1 over the W*32 threads of the block, team_bar)
+//   main: tcmd[0] = TEAM_STOP; barrier                                                      (per polygon, by the kernel)
+//   helpers: loop { barrier; read tcmd; STOP -> leave; their share of the refresh; barrier }
+// W == 1 compiles to the single-warp code (no block barriers).
+enum : uint32_t { TEAM_STOP = 0u, TEAM_REFRESH = 1u, TEAM_ITEMS = 2u };
+
+// Team barrier: named barrier 1 with an explicit thread count -- the main warp and the helper warps arrive from
+// different code, which bar.sync allows as long as whole warps arrive (unlike __syncthreads()'s convergence rule).
+template <int W>
+__device__ __forceinline__ void team_bar() {
+    asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void team_sync() {
+    if (W > 1) team_bar<W>(); else __syncwarp();
+}
+
+struct FItems {
+    uint16_t *it_node, *it_next, *it_edge, *ehead;
+    uint32_t *eul, *ctr;
+    uint32_t cap;
+};
+
+// Lane-parallel advance of every pending point's cached location and (do_items) of every pending edge's search.
+// Called by all W*32 threads of the team with the same arguments; tid = 0 .. W*32-1.
+template <int W>
+__device__ __forceinline__ void team_refresh(const FPoly& P, uint16_t* loc, uint32_t n, bool do_items, const FItems& I,
+                                             uint32_t items_end, uint32_t tid) {
+    constexpr uint32_t T = (uint32_t)W * 32u;
+    const float2* sxy = P.sxy;
+    for (uint32_t r = tid; r < n; r += T) {  // loc is in rank space
+        const uint32_t cur = loc[r];
+        if (cur != FNIL) loc[r] = (uint16_t)P.locate(r, sxy[r], cur);  // never FNIL: r is not inserted yet
+    }
+    if (do_items) {
+        // new sibling items are handled in the next round; items_end = the item count when the refresh began
+        // (read by the main warp before the team started, so every warp runs the same rounds)
+        uint32_t start = 0, end = items_end;
+        while (start < end) {
+            for (uint32_t it = start + tid; it < end; it += T) {
+                const uint32_t e = I.it_edge[it];
+                if (I.ehead[e] == FNIL) continue;  // edge already inserted
+                uint32_t node = I.it_node[it];
+                uint2 v = P.nd[node];
+                if (FPoly::type_of(v.y) == T_TRAPEZOID) continue;
+                const uint32_t ul = I.eul[e];
+                const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
+                const float2 Pu = sxy[up], Pl = sxy[lo];
+                do {
+                    bool both;
+                    const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
+                    if (both) {
+                        const uint32_t nw = atomicAdd(&I.ctr[0], 1u);
+                        if (nw >= I.cap) {
+                            I.ctr[1] = 1;
+                            break;
+                        }
+                        I.it_node[nw] = (uint16_t)(v.x >> 16);  // child2, searched after everything under child1
+                        I.it_edge[nw] = (uint16_t)e;
+                        I.it_next[nw] = I.it_next[it];
+                        I.it_next[it] = (uint16_t)nw;
+                    }
+                    node = next;
+                    v = P.nd[node];
+                } while (FPoly::type_of(v.y) != T_TRAPEZOID);
+                I.it_node[it] = (uint16_t)node;
+            }
+            team_sync<W>();  // every append of this round is done
+            start = end;
+            end = min(I.ctr[0], I.cap);
+            if (W > 1) team_bar<W>();  // everyone has read the counter before the next round moves it
+        }
+    }
+}
+
+__device__ __forceinline__ FItems fast_items(unsigned char* ws, const FLayout& L, const FCaps& caps) {
+    FItems I;
+    I.it_node = reinterpret_cast<uint16_t*>(ws + L.it_node);
+    I.it_next = reinterpret_cast<uint16_t*>(ws + L.it_next);
+    I.it_edge = reinterpret_cast<uint16_t*>(ws + L.it_edge);
+    I.ehead = reinterpret_cast<uint16_t*>(ws + L.ehead);
+    I.eul = reinterpret_cast<uint32_t*>(ws + L.eul);
+    I.ctr = reinterpret_cast<uint32_t*>(ws + L.ctr);  // [0] items allocated, [1] pool overflow flag
+    I.cap = caps.item_cap;
+    return I;
+}
+
+// The helper warps of a team: serve refresh requests of the main warp until it says stop.
+template <int W>
+__device__ void team_helper(unsigned char* ws, const FCaps caps, const FLayout L, const uint32_t* tcmd) {
+    FPoly P;
+    P.sxy = reinterpret_cast<const float2*>(ws + L.sxy);
+    P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
+    uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
+    const FItems I = fast_items(ws, L, caps);
+    for (;;) {
+        team_bar<W>();
+        const uint32_t cmd = tcmd[0];
+        if (cmd == TEAM_STOP) break;
+        team_refresh<W>(P, loc, tcmd[1], (cmd & TEAM_ITEMS) != 0u, I, tcmd[2], threadIdx.x);
+        team_bar<W>();
+    }
+}
+
+// All 32 lanes of the main warp call this.  Returns F_DONE with *res filled, or a requeue code.
+template <int W>
 __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps,
-                                    const FLayout L, Result* res) {
+                                    const FLayout L, Result* res, uint32_t* tcmd) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t p0 = a.first_point[pi] - a.point_base;
@@ -540,13 +652,17 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
 
     // ---- conflict lists of the pending edges (items tier) ---------------------------------------------
     const bool use_items = caps.item_cap != 0;
-    const uint32_t item_period = 4u * ((n + 63u) / 64u);  // measured best of 1/2/4/8 on n <= 1024
-    uint16_t* it_node = reinterpret_cast<uint16_t*>(ws + L.it_node);
-    uint16_t* it_next = reinterpret_cast<uint16_t*>(ws + L.it_next);
-    uint16_t* it_edge = reinterpret_cast<uint16_t*>(ws + L.it_edge);
-    uint16_t* ehead = reinterpret_cast<uint16_t*>(ws + L.ehead);
-    uint32_t* eul = reinterpret_cast<uint32_t*>(ws + L.eul);
-    uint32_t* ctr = reinterpret_cast<uint32_t*>(ws + L.ctr);  // [0] items allocated, [1] pool overflow flag
+#ifndef MR_TEAM_LOC_DIV
+#define MR_TEAM_LOC_DIV 64u
+#endif
+#ifndef MR_TEAM_ITEM_MULT
+#define MR_TEAM_ITEM_MULT 4u
+#endif
+    const uint32_t refresh_every = W > 1 ? (n + MR_TEAM_LOC_DIV - 1u) / MR_TEAM_LOC_DIV : (n + 63u) / 64u;
+    const uint32_t item_period = (W > 1 ? MR_TEAM_ITEM_MULT : 4u) * refresh_every;  // single warp: measured best of 1/2/4/8 on n <= 1024
+    const FItems I = fast_items(ws, L, caps);
+    uint16_t *const it_node = I.it_node, *const it_next = I.it_next, *const it_edge = I.it_edge, *const ehead = I.ehead;
+    uint32_t *const eul = I.eul, *const ctr = I.ctr;
     if (use_items) {
         for (uint32_t e = lane; e < n; e += 32) {  // every edge starts with one item at the root
             const uint32_t pa = rk[e], pb = rk[e + 1u == n ? 0u : e + 1u];
@@ -585,60 +701,27 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         par_next = par_node + par_cap;
     }
 
-    const uint32_t refresh_every = (n + 63u) / 64u;
     const bool ur_simple = ur_offset < n && ur_prime < n;
     uint32_t ur_edge = ur_offset;
     bool ok = true;
     for (uint32_t at = 0; at < n && ok; ++at) {  // :484-494
         if (at % refresh_every == 0) {
-            // lane-parallel advance of every pending point's cached location (loc is in rank space)
-            for (uint32_t r = lane; r < n; r += 32) {
-                const uint32_t cur = loc[r];
-                if (cur != FNIL) loc[r] = (uint16_t)P.locate(r, sxy[r], cur);  // never FNIL: r is not inserted yet
-            }
-            if (use_items && (at % item_period == 0)) {
-                // lane-parallel advance of every pending edge's search; new sibling items are handled in
-                // the next round
-                uint32_t start = 0, end = ctr[0];
-                while (start < end) {
-                    for (uint32_t it = start + lane; it < end; it += 32) {
-                        const uint32_t e = it_edge[it];
-                        if (ehead[e] == FNIL) continue;  // edge already inserted
-                        uint32_t node = it_node[it];
-                        uint2 v = P.nd[node];
-                        if (FPoly::type_of(v.y) == T_TRAPEZOID) continue;
-                        const uint32_t ul = eul[e];
-                        const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
-                        const float2 Pu = sxy[up], Pl = sxy[lo];
-                        do {
-                            bool both;
-                            const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
-                            if (both) {
-                                const uint32_t nw = atomicAdd(&ctr[0], 1u);
-                                if (nw >= caps.item_cap) {
-                                    ctr[1] = 1;
-                                    break;
-                                }
-                                it_node[nw] = (uint16_t)(v.x >> 16);  // child2, searched after everything under child1
-                                it_edge[nw] = (uint16_t)e;
-                                it_next[nw] = it_next[it];
-                                it_next[it] = (uint16_t)nw;
-                            }
-                            node = next;
-                            v = P.nd[node];
-                        } while (FPoly::type_of(v.y) != T_TRAPEZOID);
-                        it_node[it] = (uint16_t)node;
-                    }
-                    __syncwarp();
-                    start = end;
-                    end = min(ctr[0], caps.item_cap);
+            const bool do_items = use_items && (at % item_period == 0);
+            const uint32_t items_end = do_items ? ctr[0] : 0u;
+            if (W > 1) {
+                if (lane == 0) {
+                    tcmd[0] = TEAM_REFRESH | (do_items ? TEAM_ITEMS : 0u);
+                    tcmd[1] = n;
+                    tcmd[2] = items_end;
                 }
-                if (ctr[1]) {  // pool exhausted: the next tier redoes this polygon with the literal search
-                    P.requeue = true;
-                    break;
-                }
+                team_bar<W>();
             }
-            __syncwarp();
+            team_refresh<W>(P, loc, n, do_items, I, items_end, lane);
+            team_sync<W>();
+            if (do_items && ctr[1]) {  // pool exhausted: the next tier redoes this polygon with the literal search
+                P.requeue = true;
+                break;
+            }
         }
         // unirand.zig:16: (at * prime + offset) % top in u32 arithmetic.  With offset, prime < n (always so for
         // unirand_seed's own output) the sequence is an add-and-wrap; explicit pairs outside that keep the formula.
