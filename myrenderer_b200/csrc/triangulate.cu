@@ -531,17 +531,17 @@ struct Sink {
         }
     }
     // zero vertices [k0, k1) cooperatively
-    __device__ void zero(uint32_t k0, uint32_t k1, uint32_t lane) const {
+    __device__ void zero(uint32_t k0, uint32_t k1, uint32_t lane, uint32_t nthreads = 32u) const {
         if (k1 <= k0) return;
         if (fast32) {
-            for (uint32_t k = k0 + lane; k < k1; k += 32)
+            for (uint32_t k = k0 + lane; k < k1; k += nthreads)
                 asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(base + (size_t)k * 32),
                              "f"(0.0f)
                              : "memory");
         } else {
             uint32_t* w = reinterpret_cast<uint32_t*>(base + (size_t)k0 * stride);
             const size_t words = (size_t)(k1 - k0) * stride / 4;
-            for (size_t i = lane; i < words; i += 32) w[i] = 0u;
+            for (size_t i = lane; i < words; i += nthreads) w[i] = 0u;
         }
     }
 };
@@ -1059,7 +1059,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
 template <int W>
 __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, int c) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint32_t tcmd[4];  // [0] command, [1] n, [2] item count at refresh start, [3] queue index
+    __shared__ TeamShared ts;
     const FCaps caps = fast_caps(c, false);
     const FLayout L = fast_layout(caps);
     const uint32_t lane = threadIdx.x & 31u;
@@ -1067,15 +1067,15 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
     const uint32_t begin = a.class_begin[c];
     const uint32_t count = a.class_end[c] - begin;
     for (;;) {
-        if (threadIdx.x == 0) tcmd[3] = atomicAdd(&a.queue_head[c], 1u);
+        if (threadIdx.x == 0) ts.qidx = atomicAdd(&a.queue_head[c], 1u);
         __syncthreads();
-        const uint32_t idx = tcmd[3];
+        const uint32_t idx = ts.qidx;
         if (idx >= count) break;
+        const uint32_t pi = a.order[begin + idx];
         if (main_warp) {
-            const uint32_t pi = a.order[begin + idx];
             Result r;
-            const int rc = process_polygon_fast<W>(a, pi, smem, caps, L, &r, tcmd);
-            if (lane == 0) tcmd[0] = TEAM_STOP;
+            const int rc = process_polygon_fast<W>(a, pi, smem, caps, L, &r, &ts);
+            if (lane == 0) ts.cmd = TEAM_STOP;
             team_bar<W>();
             if (rc == F_DONE) {
                 write_result(a, pi, r);
@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
                     a.general_list[atomicAdd(a.general_count, 1u)] = pi;
             }
         } else {
-            team_helper<W>(smem, caps, L, tcmd);
+            team_helper<W>(a, pi, smem, caps, L, &ts);
         }
     }
 }

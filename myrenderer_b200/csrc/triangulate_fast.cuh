@@ -401,14 +401,26 @@ struct FPoly {
 // In the classes above 128 points a polygon's workspace is so large that only a few polygons fit an SM, and
 // a lone warp issues one instruction every ~6 cycles: most issue slots of the SM sit idle.  There a block of
 // W warps works on ONE polygon: warp 0 (the main warp) runs the algorithm, the other warps join it for the
-// lane-parallel phases -- the refresh of the point-location caches and of the pending edges' conflict lists --
-// which are loops over independent entries.  Protocol (all block-wide barriers, same count on every warp):
-//   main: tcmd[0] = TEAM_REFRESH|flags; barrier; its share of the refresh; barrier         (per refresh)
+// lane-parallel phases -- loading and ranking the points, the refresh of the point-location caches and of the
+// pending edges' conflict lists, and the final group/sort/emit -- which are loops over independent entries.  Protocol (all block-wide barriers, same count on every warp):
+//   main: ts->cmd = phase (LOAD, REFRESH|flags, FINISH); barrier; its share of the phase  (per phase; the phase
+//         functions contain their own barriers and are called by every warp with the same arguments)
 // ("barrier" = named barrier 1 over the W*32 threads of the block, team_bar)
-//   main: tcmd[0] = TEAM_STOP; barrier                                                      (per polygon, by the kernel)
-//   helpers: loop { barrier; read tcmd; STOP -> leave; their share of the refresh; barrier }
+//   main: ts->cmd = TEAM_STOP; barrier                                                     (per polygon, by the kernel)
+//   helpers: loop { barrier; read ts->cmd; STOP -> leave; their share of the phase }
 // W == 1 compiles to the single-warp code (no block barriers).
-enum : uint32_t { TEAM_STOP = 0u, TEAM_REFRESH = 1u, TEAM_ITEMS = 2u };
+enum : uint32_t { TEAM_STOP = 0u, TEAM_REFRESH = 1u, TEAM_ITEMS = 2u, TEAM_LOAD = 4u, TEAM_FINISH = 8u };
+constexpr int TEAM_MAX_WARPS = 4;
+// block-shared words of a team (one polygon per block in the team kernel)
+struct TeamShared {
+    uint32_t cmd;        // TEAM_* of the phase the main warp is entering
+    uint32_t n;          // points of the current polygon
+    uint32_t arg0, arg1; // REFRESH: item count at start; FINISH: adds A, mountains M
+    uint32_t qidx;       // queue position of the current polygon
+    uint32_t flag0, flag1;  // LOAD: non-finite seen, tie seen; FINISH: not-acute seen
+    uint32_t T;          // FINISH: triangles
+    float part[TEAM_MAX_WARPS][4];  // FINISH: per-warp bbox partials {min x, max x, last y, has last}
+};
 
 // Team barrier: named barrier 1 with an explicit thread count -- the main warp and the helper warps arrive from
 // different code, which bar.sync allows as long as whole warps arrive (unlike __syncthreads()'s convergence rule).
@@ -479,6 +491,287 @@ __device__ __forceinline__ void team_refresh(const FPoly& P, uint16_t* loc, uint
     }
 }
 
+
+// Load, validate and rank a polygon's points; all W*32 threads of the team call it (tid = 0 .. W*32-1).
+// Returns 0 ok, 1 non-finite coordinate, 2 coincident points (same value on every thread).
+template <int W>
+__device__ __forceinline__ int team_load_rank(const float2* src, unsigned char* ws, const FLayout& L, uint32_t n, uint32_t tid,
+                                              TeamShared* ts) {
+    constexpr uint32_t T = (uint32_t)W * 32u;
+    float2* sxy = reinterpret_cast<float2*>(ws + L.sxy);
+    uint16_t* orig = reinterpret_cast<uint16_t*>(ws + L.orig);
+    uint16_t* rk = reinterpret_cast<uint16_t*>(ws + L.rk);
+    uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
+    // Original coordinates are staged in the node arena (free until the trapezoidation starts).
+    float2* raw = reinterpret_cast<float2*>(ws + L.nodes);
+    bool finite = true;
+    for (uint32_t i = tid; i < n; i += T) {
+        const float2 v = __ldg(src + i);
+        raw[i] = v;
+        finite = finite && isfinite(v.x) && isfinite(v.y);
+    }
+    if (W > 1) {
+        if (!finite) ts->flag0 = 1u;
+        team_bar<W>();
+        if (ts->flag0) return 1;
+    } else {
+        __syncwarp();
+        if (!__all_sync(0xFFFFFFFFu, finite)) return 1;
+    }
+    // rank = position in the (y, x) order (point_is_above, Triangulation.zig:128-136): bitonic sort of
+    // order-preserving 64-bit keys, staged behind the raw coordinates in the node arena (O(n log^2 n);
+    // the O(n^2) count it replaces was 29 % of the instructions at n = 1024).  -0 and +0 compare equal
+    // as floats, so the key maps both to +0; the emitted coordinates still come from `raw`.
+    uint32_t n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + L.nodes) + n;  // 8n + 8*n2 <= 8*node_cap
+    uint16_t* kidx = reinterpret_cast<uint16_t*>(ws + L.add_pp);                        // 2*n2 <= 4n <= 4*add_cap
+    for (uint32_t i = tid; i < n2; i += T) {
+        unsigned long long k = ~0ull;  // padding sorts last
+        if (i < n) {
+            const float2 v = raw[i];
+            uint32_t by = __float_as_uint(v.y == 0.0f ? 0.0f : v.y), bx = __float_as_uint(v.x == 0.0f ? 0.0f : v.x);
+            by ^= (by >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+            bx ^= (bx >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+            k = ((unsigned long long)by << 32) | bx;
+        }
+        keys[i] = k;
+        kidx[i] = (uint16_t)i;
+    }
+    team_sync<W>();
+    for (uint32_t size = 2; size <= n2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (n2 >> 1); t += T) {
+                const uint32_t lo_i = ((t & ~(stride - 1u)) << 1) | (t & (stride - 1u));
+                const uint32_t hi_i = lo_i | stride;
+                const bool up_dir = (lo_i & size) == 0u;
+                const unsigned long long ka = keys[lo_i], kb = keys[hi_i];
+                if ((ka > kb) == up_dir) {
+                    keys[lo_i] = kb;
+                    keys[hi_i] = ka;
+                    const uint16_t ia = kidx[lo_i];
+                    kidx[lo_i] = kidx[hi_i];
+                    kidx[hi_i] = ia;
+                }
+            }
+            team_sync<W>();
+        }
+    }
+    bool tie = false;
+    for (uint32_t r = tid; r < n; r += T) {
+        if (r + 1u < n && keys[r] == keys[r + 1u]) tie = true;
+        rk[kidx[r]] = (uint16_t)r;
+    }
+    if (W > 1) {
+        if (tie) ts->flag1 = 1u;
+        team_bar<W>();
+        if (ts->flag1) return 2;
+    } else {
+        if (__any_sync(0xFFFFFFFFu, tie)) return 2;
+        __syncwarp();
+    }
+    for (uint32_t i = tid; i < n; i += T) {
+        const uint32_t r = rk[i];
+        sxy[r] = raw[i];
+        orig[r] = (uint16_t)i;
+        loc[i] = 0;  // every point starts at the root
+    }
+    team_sync<W>();
+    return 0;
+}
+
+__device__ __forceinline__ Sink fast_sink(const BatchArgs& a, uint32_t pi, uint32_t* cap_tri) {
+    const uint64_t t0 = a.first_tri[pi] - a.tri_base;
+    *cap_tri = (uint32_t)(a.first_tri[pi + 1] - a.first_tri[pi]);
+    Sink sink;
+    sink.base = a.vtx_out + t0 * 3u * a.stride;
+    sink.cap_vtx = *cap_tri * 3u;
+    sink.stride = a.stride;
+    sink.off_x = a.off_x;
+    sink.off_c = a.off_c;
+    sink.fast32 = a.fast32;
+    return sink;
+}
+
+// Last phase: the A adds (add_pp, add_m, mstart, zeroed mcount are in place) are grouped by mountain, every
+// mountain is sorted (:555), and the emission loop :558-586 runs in closed form.  All W*32 threads of the team
+// call it; only the main warp's *res is filled.  Returns F_DONE or F_REQUEUE_GENERAL (same on every thread).
+template <int W>
+__device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, unsigned char* ws, const FCaps& caps,
+                                           const FLayout& L, uint32_t A, uint32_t tid, TeamShared* ts, Result* res) {
+    constexpr uint32_t TT = (uint32_t)W * 32u;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float2* sxy = reinterpret_cast<const float2*>(ws + L.sxy);
+    const uint16_t* orig = reinterpret_cast<const uint16_t*>(ws + L.orig);
+    const uint32_t* add_pp = reinterpret_cast<const uint32_t*>(ws + L.add_pp);
+    const uint16_t* add_m = reinterpret_cast<const uint16_t*>(ws + L.add_m);
+    uint32_t* mcount = reinterpret_cast<uint32_t*>(ws + L.mcount);
+    const uint16_t* mstart = reinterpret_cast<const uint16_t*>(ws + L.mstart);
+
+    // ---- group entries by mountain, stable sort by (rank, append position)  (:555) ----------------
+    // sort arrays alias the node arena: Gpos, cum, Gid, Gm, S -- u16 each, E = 2A entries
+    const uint32_t E = 2u * A;
+    const size_t ecap = (size_t)caps.add_cap * 2;
+    uint16_t* Gpos = reinterpret_cast<uint16_t*>(ws + L.nodes);
+    uint16_t* cum = Gpos + ecap;
+    uint16_t* Gid = cum + ecap;
+    uint16_t* Gm = Gid + ecap;
+    uint16_t* S = Gm + ecap;
+    for (uint32_t ai = tid; ai < A; ai += TT) {
+        const uint32_t m = add_m[ai];
+        const uint32_t pp = add_pp[ai];
+        const uint32_t slot = mstart[m] + atomicAdd(&mcount[m], 2u);
+        Gpos[slot] = (uint16_t)(2u * ai);  // p1 appended first (:60)
+        Gid[slot] = (uint16_t)(pp & FNIL14);
+        Gpos[slot + 1] = (uint16_t)(2u * ai + 1u);  // then p2 (:61)
+        Gid[slot + 1] = (uint16_t)(pp >> 16);
+        Gm[slot] = (uint16_t)m;
+        Gm[slot + 1] = (uint16_t)m;
+    }
+    team_sync<W>();
+    for (uint32_t g = tid; g < E; g += TT) {
+        const uint32_t m = Gm[g];
+        const uint32_t s = mstart[m], t = mstart[m + 1];
+        const uint32_t mykey = ((uint32_t)Gid[g] << 16) | Gpos[g];  // (rank, append position)
+        uint32_t rank = 0;
+        for (uint32_t h = s; h < t; ++h) rank += ((((uint32_t)Gid[h] << 16) | Gpos[h]) < mykey) ? 1u : 0u;
+        S[s + rank] = Gid[g];
+    }
+    team_sync<W>();
+
+    // ---- triangles: valid j, acute check, slots  (:558-586 in closed form) -------------------------
+    uint32_t T = 0;
+    if (W == 1) {
+        uint32_t running = 0;
+        bool all_acute = true;
+        for (uint32_t b = 0; b < E; b += 32) {
+            const uint32_t g = b + lane;
+            bool valid = false;
+            if (g < E) {
+                const uint32_t s = mstart[Gm[g]];
+                if (g >= s + 2u) {
+                    const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
+                    valid = (c != a1) && (c != a2);
+                    if (valid && !is_acute(sxy, c, a1, a2)) all_acute = false;
+                }
+            }
+            const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+            if (g < E) cum[g] = (uint16_t)(running + __popc(vm & (lt_mask | (1u << lane))));
+            running += __popc(vm);
+        }
+        all_acute = __all_sync(0xFFFFFFFFu, all_acute);
+        __syncwarp();
+        // a push_triangle_if_acute returned false somewhere: the literal loop of the general path decides
+        if (!all_acute) return F_REQUEUE_GENERAL;
+        T = running;
+    } else {
+        // the flags (with the acute checks) by everyone, then the ordered prefix sum by the main warp
+        bool all_acute = true;
+        for (uint32_t g = tid; g < E; g += TT) {
+            bool valid = false;
+            const uint32_t s = mstart[Gm[g]];
+            if (g >= s + 2u) {
+                const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
+                valid = (c != a1) && (c != a2);
+                if (valid && !is_acute(sxy, c, a1, a2)) all_acute = false;
+            }
+            cum[g] = valid ? 1u : 0u;
+        }
+        if (!all_acute) ts->flag0 = 1u;
+        team_bar<W>();
+        if (ts->flag0) return F_REQUEUE_GENERAL;
+        if (warp == 0) {
+            uint32_t running = 0;
+            for (uint32_t b = 0; b < E; b += 32) {
+                const uint32_t g = b + lane;
+                const bool valid = g < E && cum[g] != 0u;
+                const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+                if (g < E) cum[g] = (uint16_t)(running + __popc(vm & (lt_mask | (1u << lane))));
+                running += __popc(vm);
+            }
+            if (lane == 0) ts->T = running;
+        }
+        team_bar<W>();
+        T = ts->T;
+    }
+
+    float mn = 0.0f, mx = 0.0f, lasty = 0.0f;
+    bool has_last = false;
+    for (uint32_t g = tid; g < E; g += TT) {
+        const uint32_t m = Gm[g];
+        const uint32_t s = mstart[m], t = mstart[m + 1];
+        if (g < s + 2u) continue;
+        const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
+        if (c == a1 || c == a2) continue;
+        const uint32_t before = s ? cum[s - 1] : 0u;
+        const uint32_t slot = before + (cum[t - 1] - cum[g]);
+        // the emit order (:405-422) is defined on the original point ids
+        const uint32_t oc = orig[c], o1 = orig[a1], o2 = orig[a2];
+        uint32_t second, third;
+        if ((o1 > oc && o2 > oc) || (o1 < oc && o2 < oc)) {
+            second = o1 > o2 ? a2 : a1;
+            third = o1 > o2 ? a1 : a2;
+        } else if (o2 > oc) {
+            second = a2;
+            third = a1;
+        } else {
+            second = a1;
+            third = a2;
+        }
+        const float2 q0 = sxy[c], q1 = sxy[second], q2 = sxy[third];
+        mn = fmin_acc(fmin_acc(fmin_acc(mn, q0.x), q1.x), q2.x);
+        mx = fmax_acc(fmax_acc(fmax_acc(mx, q0.x), q1.x), q2.x);
+        if (slot == T - 1u) {
+            lasty = q2.y;
+            has_last = true;
+        }
+        if (slot < cap_tri) {
+            sink.write(3u * slot, q0);
+            sink.write(3u * slot + 1u, q1);
+            sink.write(3u * slot + 2u, q2);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        mn = fmin_acc(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+        mx = fmax_acc(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    }
+    {
+        const uint32_t lm = __ballot_sync(0xFFFFFFFFu, has_last);
+        has_last = lm != 0u;
+        lasty = lm ? __shfl_sync(0xFFFFFFFFu, lasty, __ffs(lm) - 1) : 0.0f;
+    }
+    if (T < cap_tri) sink.zero(3u * T, sink.cap_vtx, tid, TT);
+    if (W > 1) {
+        if (lane == 0) {
+            ts->part[warp][0] = mn;
+            ts->part[warp][1] = mx;
+            ts->part[warp][2] = lasty;
+            ts->part[warp][3] = has_last ? 1.0f : 0.0f;
+        }
+        team_bar<W>();
+        if (warp != 0) return F_DONE;
+        mn = mx = lasty = 0.0f;  // exactly one warp holds the last triangle (slot T-1), if there is one
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            mn = fmin_acc(mn, ts->part[w][0]);
+            mx = fmax_acc(mx, ts->part[w][1]);
+            if (ts->part[w][3] != 0.0f) lasty = ts->part[w][2];
+        }
+    }
+    uint32_t status = MR_POLY_OK;
+    if (T > cap_tri) status |= MR_POLY_OVERFLOW;
+    if (T < cap_tri) status |= MR_POLY_UNDERFILL;
+    res->b1x = mn;
+    res->b2x = mx;
+    res->b1y = T ? fmin_acc(mn, lasty) : 0.0f;
+    res->b2y = T ? fmax_acc(mx, lasty) : 0.0f;
+    res->status = status;
+    res->ntri = T < cap_tri ? T : cap_tri;
+    return F_DONE;
+}
+
 __device__ __forceinline__ FItems fast_items(unsigned char* ws, const FLayout& L, const FCaps& caps) {
     FItems I;
     I.it_node = reinterpret_cast<uint16_t*>(ws + L.it_node);
@@ -491,9 +784,10 @@ __device__ __forceinline__ FItems fast_items(unsigned char* ws, const FLayout& L
     return I;
 }
 
-// The helper warps of a team: serve refresh requests of the main warp until it says stop.
+// The helper warps of a team: join the main warp in the phase it announces, until it says stop.
 template <int W>
-__device__ void team_helper(unsigned char* ws, const FCaps caps, const FLayout L, const uint32_t* tcmd) {
+__device__ void team_helper(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps, const FLayout L,
+                            TeamShared* ts) {
     FPoly P;
     P.sxy = reinterpret_cast<const float2*>(ws + L.sxy);
     P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
@@ -501,32 +795,33 @@ __device__ void team_helper(unsigned char* ws, const FCaps caps, const FLayout L
     const FItems I = fast_items(ws, L, caps);
     for (;;) {
         team_bar<W>();
-        const uint32_t cmd = tcmd[0];
+        const uint32_t cmd = ts->cmd;
         if (cmd == TEAM_STOP) break;
-        team_refresh<W>(P, loc, tcmd[1], (cmd & TEAM_ITEMS) != 0u, I, tcmd[2], threadIdx.x);
-        team_bar<W>();
+        if (cmd & TEAM_REFRESH) {
+            team_refresh<W>(P, loc, ts->n, (cmd & TEAM_ITEMS) != 0u, I, ts->arg0, threadIdx.x);
+            team_bar<W>();
+        } else if (cmd == TEAM_LOAD) {
+            const uint64_t p0 = a.first_point[pi] - a.point_base;
+            team_load_rank<W>(reinterpret_cast<const float2*>(a.xy) + p0, ws, L, ts->n, threadIdx.x, ts);
+        } else {  // TEAM_FINISH
+            uint32_t cap_tri;
+            const Sink sink = fast_sink(a, pi, &cap_tri);
+            team_finish<W>(sink, cap_tri, ws, caps, L, ts->arg0, threadIdx.x, ts, nullptr);
+        }
     }
 }
 
 // All 32 lanes of the main warp call this.  Returns F_DONE with *res filled, or a requeue code.
 template <int W>
 __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps,
-                                    const FLayout L, Result* res, uint32_t* tcmd) {
+                                    const FLayout L, Result* res, TeamShared* ts) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t p0 = a.first_point[pi] - a.point_base;
     const uint64_t np64 = a.first_point[pi + 1] - a.first_point[pi];
-    const uint64_t t0 = a.first_tri[pi] - a.tri_base;
-    const uint32_t cap_tri = (uint32_t)(a.first_tri[pi + 1] - a.first_tri[pi]);
     const uint32_t n = (uint32_t)(np64 > 0xFFFFFFFFull ? 0xFFFFFFFFull : np64);
-
-    Sink sink;
-    sink.base = a.vtx_out + t0 * 3u * a.stride;
-    sink.cap_vtx = cap_tri * 3u;
-    sink.stride = a.stride;
-    sink.off_x = a.off_x;
-    sink.off_c = a.off_c;
-    sink.fast32 = a.fast32;
+    uint32_t cap_tri;
+    const Sink sink = fast_sink(a, pi, &cap_tri);
 
     res->status = MR_POLY_OK;
     res->ntri = 0;
@@ -550,79 +845,24 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     uint16_t* rk = reinterpret_cast<uint16_t*>(ws + L.rk);
     uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
 
-    // ---- load, validate, rank -------------------------------------------------------------------
-    // Original coordinates are staged in the node arena (free until the trapezoidation starts).
-    float2* raw = reinterpret_cast<float2*>(ws + L.nodes);
-    bool finite = true;
+    // ---- load, validate, rank (all warps of the team) ------------------------------------------------
+    if (W > 1) {
+        if (lane == 0) {
+            ts->cmd = TEAM_LOAD;
+            ts->n = n;
+            ts->flag0 = ts->flag1 = 0u;
+        }
+        team_bar<W>();
+    }
     {
-        const float2* src = reinterpret_cast<const float2*>(a.xy) + p0;
-        for (uint32_t i = lane; i < n; i += 32) {
-            const float2 v = __ldg(src + i);
-            raw[i] = v;
-            finite = finite && isfinite(v.x) && isfinite(v.y);
+        const int lr = team_load_rank<W>(reinterpret_cast<const float2*>(a.xy) + p0, ws, L, n, lane, ts);
+        if (lr == 1) {
+            res->status = MR_POLY_NONFINITE;
+            sink.zero(0, sink.cap_vtx, lane);
+            return F_DONE;
         }
+        if (lr == 2) return F_REQUEUE_GENERAL;  // coincident points: general path
     }
-    __syncwarp();
-    if (!__all_sync(0xFFFFFFFFu, finite)) {
-        res->status = MR_POLY_NONFINITE;
-        sink.zero(0, sink.cap_vtx, lane);
-        return F_DONE;
-    }
-    // rank = position in the (y, x) order (point_is_above, Triangulation.zig:128-136): warp bitonic sort of
-    // order-preserving 64-bit keys, staged behind the raw coordinates in the node arena (O(n log^2 n);
-    // the O(n^2) count it replaces was 29 % of the instructions at n = 1024).  -0 and +0 compare equal
-    // as floats, so the key maps both to +0; the emitted coordinates still come from `raw`.
-    {
-        uint32_t n2 = 32;
-        while (n2 < n) n2 <<= 1;
-        unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + L.nodes) + n;  // 8n + 8*n2 <= 8*node_cap
-        uint16_t* kidx = reinterpret_cast<uint16_t*>(ws + L.add_pp);                        // 2*n2 <= 4n <= 4*add_cap
-        for (uint32_t i = lane; i < n2; i += 32) {
-            unsigned long long k = ~0ull;  // padding sorts last
-            if (i < n) {
-                const float2 v = raw[i];
-                uint32_t by = __float_as_uint(v.y == 0.0f ? 0.0f : v.y), bx = __float_as_uint(v.x == 0.0f ? 0.0f : v.x);
-                by ^= (by >> 31) ? 0xFFFFFFFFu : 0x80000000u;
-                bx ^= (bx >> 31) ? 0xFFFFFFFFu : 0x80000000u;
-                k = ((unsigned long long)by << 32) | bx;
-            }
-            keys[i] = k;
-            kidx[i] = (uint16_t)i;
-        }
-        __syncwarp();
-        for (uint32_t size = 2; size <= n2; size <<= 1) {
-            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                for (uint32_t t = lane; t < (n2 >> 1); t += 32) {
-                    const uint32_t lo_i = ((t & ~(stride - 1u)) << 1) | (t & (stride - 1u));
-                    const uint32_t hi_i = lo_i | stride;
-                    const bool up_dir = (lo_i & size) == 0u;
-                    const unsigned long long ka = keys[lo_i], kb = keys[hi_i];
-                    if ((ka > kb) == up_dir) {
-                        keys[lo_i] = kb;
-                        keys[hi_i] = ka;
-                        const uint16_t ia = kidx[lo_i];
-                        kidx[lo_i] = kidx[hi_i];
-                        kidx[hi_i] = ia;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        bool tie = false;
-        for (uint32_t r = lane; r < n; r += 32) {
-            if (r + 1u < n && keys[r] == keys[r + 1u]) tie = true;
-            rk[kidx[r]] = (uint16_t)r;
-        }
-        if (__any_sync(0xFFFFFFFFu, tie)) return F_REQUEUE_GENERAL;  // coincident points: general path
-    }
-    __syncwarp();
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t r = rk[i];
-        sxy[r] = raw[i];
-        orig[r] = (uint16_t)i;
-        loc[i] = 0;  // every point starts at the root
-    }
-    __syncwarp();
 
     // ---- unirand (unirand.zig:12-50) -------------------------------------------------------------
     uint32_t ur_offset, ur_prime;
@@ -710,9 +950,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             const uint32_t items_end = do_items ? ctr[0] : 0u;
             if (W > 1) {
                 if (lane == 0) {
-                    tcmd[0] = TEAM_REFRESH | (do_items ? TEAM_ITEMS : 0u);
-                    tcmd[1] = n;
-                    tcmd[2] = items_end;
+                    ts->cmd = TEAM_REFRESH | (do_items ? TEAM_ITEMS : 0u);
+                    ts->arg0 = items_end;
                 }
                 team_bar<W>();
             }
@@ -955,119 +1194,15 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     for (uint32_t i = lane; i < M; i += 32) mcount[i] = 0u;
     __syncwarp();
 
-    // ---- group entries by mountain, stable sort by (rank, append position)  (:555) ----------------
-    // sort arrays alias the node arena: Gpos, cum, Gid, Gm, S -- u16 each, E = 2A entries
-    const uint32_t E = 2u * A;
-    const size_t ecap = (size_t)caps.add_cap * 2;
-    uint16_t* Gpos = reinterpret_cast<uint16_t*>(ws + L.nodes);
-    uint16_t* cum = Gpos + ecap;
-    uint16_t* Gid = cum + ecap;
-    uint16_t* Gm = Gid + ecap;
-    uint16_t* S = Gm + ecap;
-    for (uint32_t ai = lane; ai < A; ai += 32) {
-        const uint32_t m = add_m[ai];
-        const uint32_t pp = add_pp[ai];
-        const uint32_t slot = mstart[m] + atomicAdd(&mcount[m], 2u);
-        Gpos[slot] = (uint16_t)(2u * ai);  // p1 appended first (:60)
-        Gid[slot] = (uint16_t)(pp & FNIL14);
-        Gpos[slot + 1] = (uint16_t)(2u * ai + 1u);  // then p2 (:61)
-        Gid[slot + 1] = (uint16_t)(pp >> 16);
-        Gm[slot] = (uint16_t)m;
-        Gm[slot + 1] = (uint16_t)m;
+    // ---- group, sort, emit (all warps of the team) ---------------------------------------------------
+    if (W > 1) {
+        if (lane == 0) {
+            ts->cmd = TEAM_FINISH;
+            ts->arg0 = A;
+            ts->flag0 = 0u;
+        }
+        team_bar<W>();
     }
-    __syncwarp();
-    for (uint32_t g = lane; g < E; g += 32) {
-        const uint32_t m = Gm[g];
-        const uint32_t s = mstart[m], t = mstart[m + 1];
-        const uint32_t mykey = ((uint32_t)Gid[g] << 16) | Gpos[g];  // (rank, append position)
-        uint32_t rank = 0;
-        for (uint32_t h = s; h < t; ++h) rank += ((((uint32_t)Gid[h] << 16) | Gpos[h]) < mykey) ? 1u : 0u;
-        S[s + rank] = Gid[g];
-    }
-    __syncwarp();
-
-    // ---- triangles: valid j, acute check, slots  (:558-586 in closed form) -------------------------
-    uint32_t running = 0;
-    bool all_acute = true;
-    for (uint32_t b = 0; b < E; b += 32) {
-        const uint32_t g = b + lane;
-        bool valid = false;
-        if (g < E) {
-            const uint32_t s = mstart[Gm[g]];
-            if (g >= s + 2u) {
-                const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
-                valid = (c != a1) && (c != a2);
-                if (valid && !is_acute(sxy, c, a1, a2)) all_acute = false;
-            }
-        }
-        const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
-        if (g < E) cum[g] = (uint16_t)(running + __popc(vm & (lt_mask | (1u << lane))));
-        running += __popc(vm);
-    }
-    all_acute = __all_sync(0xFFFFFFFFu, all_acute);
-    __syncwarp();
-
-    if (all_acute) {
-        const uint32_t T = running;
-        float mn = 0.0f, mx = 0.0f, lasty = 0.0f;
-        bool has_last = false;
-        for (uint32_t g = lane; g < E; g += 32) {
-            const uint32_t m = Gm[g];
-            const uint32_t s = mstart[m], t = mstart[m + 1];
-            if (g < s + 2u) continue;
-            const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
-            if (c == a1 || c == a2) continue;
-            const uint32_t before = s ? cum[s - 1] : 0u;
-            const uint32_t slot = before + (cum[t - 1] - cum[g]);
-            // the emit order (:405-422) is defined on the original point ids
-            const uint32_t oc = orig[c], o1 = orig[a1], o2 = orig[a2];
-            uint32_t second, third;
-            if ((o1 > oc && o2 > oc) || (o1 < oc && o2 < oc)) {
-                second = o1 > o2 ? a2 : a1;
-                third = o1 > o2 ? a1 : a2;
-            } else if (o2 > oc) {
-                second = a2;
-                third = a1;
-            } else {
-                second = a1;
-                third = a2;
-            }
-            const float2 q0 = sxy[c], q1 = sxy[second], q2 = sxy[third];
-            mn = fmin_acc(fmin_acc(fmin_acc(mn, q0.x), q1.x), q2.x);
-            mx = fmax_acc(fmax_acc(fmax_acc(mx, q0.x), q1.x), q2.x);
-            if (slot == T - 1u) {
-                lasty = q2.y;
-                has_last = true;
-            }
-            if (slot < cap_tri) {
-                sink.write(3u * slot, q0);
-                sink.write(3u * slot + 1u, q1);
-                sink.write(3u * slot + 2u, q2);
-            }
-        }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            mn = fmin_acc(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-            mx = fmax_acc(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
-        }
-        {
-            const uint32_t lm = __ballot_sync(0xFFFFFFFFu, has_last);
-            lasty = lm ? __shfl_sync(0xFFFFFFFFu, lasty, __ffs(lm) - 1) : 0.0f;
-        }
-        uint32_t status = MR_POLY_OK;
-        if (T > cap_tri) status |= MR_POLY_OVERFLOW;
-        if (T < cap_tri) {
-            status |= MR_POLY_UNDERFILL;
-            sink.zero(3u * T, sink.cap_vtx, lane);
-        }
-        res->b1x = mn;
-        res->b2x = mx;
-        res->b1y = T ? fmin_acc(mn, lasty) : 0.0f;
-        res->b2y = T ? fmax_acc(mx, lasty) : 0.0f;
-        res->status = status;
-        res->ntri = T < cap_tri ? T : cap_tri;
-        return F_DONE;
-    }
-    // a push_triangle_if_acute returned false somewhere: the literal loop of the general path decides
-    return F_REQUEUE_GENERAL;
+    return team_finish<W>(sink, cap_tri, ws, caps, L, A, lane, ts, res);
 }
+
