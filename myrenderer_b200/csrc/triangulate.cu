@@ -31,7 +31,9 @@ constexpr int MAX_WARPS_PER_BLOCK = 4;
 
 __host__ __device__ inline uint32_t class_nmax(int c) { return 64u << c; }
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
-inline int team_warps(int c) { return c >= 3 ? 4 : (c == 2 ? 2 : 1); }
+// (measured on B200: 2/4/8 for the 256/512/1024-point classes; 8 warps in the 512 class or 4 in the 256 class lose
+// polygons in flight to the register file and are slower)
+inline int team_warps(int c) { return c == 4 ? 8 : (c == 3 ? 4 : (c == 2 ? 2 : 1)); }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
     while (c < NUM_CLASSES - 1 && n > class_nmax(c)) ++c;
@@ -1353,7 +1355,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             if (team > 1) {  // one polygon per block, `team` warps per polygon
                 const size_t smem = L.total;
                 if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = team == 2 ? triangulate_team_k<2> : triangulate_team_k<4>;
+                auto kern = team == 2 ? triangulate_team_k<2> : (team == 4 ? triangulate_team_k<4> : triangulate_team_k<8>);
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
                 MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));

@@ -410,7 +410,7 @@ struct FPoly {
 //   helpers: loop { barrier; read ts->cmd; STOP -> leave; their share of the phase }
 // W == 1 compiles to the single-warp code (no block barriers).
 enum : uint32_t { TEAM_STOP = 0u, TEAM_REFRESH = 1u, TEAM_ITEMS = 2u, TEAM_LOAD = 4u, TEAM_FINISH = 8u };
-constexpr int TEAM_MAX_WARPS = 4;
+constexpr int TEAM_MAX_WARPS = 8;
 // block-shared words of a team (one polygon per block in the team kernel)
 struct TeamShared {
     uint32_t cmd;        // TEAM_* of the phase the main warp is entering
@@ -439,13 +439,46 @@ struct FItems {
     uint32_t cap;
 };
 
+// One pending item of the conflict lists: continue its walk until it sits on a trapezoid; a straddled point node
+// links a sibling item right behind it (handled by a later round).
+__device__ __forceinline__ void advance_item(const FPoly& P, const FItems& I, uint32_t it) {
+    const uint32_t e = I.it_edge[it];
+    if (I.ehead[e] == FNIL) return;  // edge already inserted
+    uint32_t node = I.it_node[it];
+    uint2 v = P.nd[node];
+    if (FPoly::type_of(v.y) == T_TRAPEZOID) return;
+    const uint32_t ul = I.eul[e];
+    const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
+    const float2 Pu = P.sxy[up], Pl = P.sxy[lo];
+    do {
+        bool both;
+        const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
+        if (both) {
+            const uint32_t nw = atomicAdd(&I.ctr[0], 1u);
+            if (nw >= I.cap) {
+                I.ctr[1] = 1;
+                break;
+            }
+            I.it_node[nw] = (uint16_t)(v.x >> 16);  // child2, searched after everything under child1
+            I.it_edge[nw] = (uint16_t)e;
+            I.it_next[nw] = I.it_next[it];
+            I.it_next[it] = (uint16_t)nw;
+        }
+        node = next;
+        v = P.nd[node];
+    } while (FPoly::type_of(v.y) != T_TRAPEZOID);
+    I.it_node[it] = (uint16_t)node;
+}
+
 // Lane-parallel advance of every pending point's cached location and (do_items) of every pending edge's search.
 // Called by all W*32 threads of the team with the same arguments; tid = 0 .. W*32-1.
 template <int W>
-__device__ __forceinline__ void team_refresh(const FPoly& P, uint16_t* loc, uint32_t n, bool do_items, const FItems& I,
-                                             uint32_t items_end, uint32_t tid) {
+__device__ __forceinline__ void team_refresh(const float2* sxy, uint2* nd, uint16_t* loc, uint32_t n, bool do_items,
+                                             const FItems I, uint32_t items_end, uint32_t tid) {
     constexpr uint32_t T = (uint32_t)W * 32u;
-    const float2* sxy = P.sxy;
+    FPoly P;  // only the immutable views are used here (locate, dfs_step)
+    P.sxy = sxy;
+    P.nd = nd;
     for (uint32_t r = tid; r < n; r += T) {  // loc is in rank space
         const uint32_t cur = loc[r];
         if (cur != FNIL) loc[r] = (uint16_t)P.locate(r, sxy[r], cur);  // never FNIL: r is not inserted yet
@@ -455,34 +488,7 @@ __device__ __forceinline__ void team_refresh(const FPoly& P, uint16_t* loc, uint
         // (read by the main warp before the team started, so every warp runs the same rounds)
         uint32_t start = 0, end = items_end;
         while (start < end) {
-            for (uint32_t it = start + tid; it < end; it += T) {
-                const uint32_t e = I.it_edge[it];
-                if (I.ehead[e] == FNIL) continue;  // edge already inserted
-                uint32_t node = I.it_node[it];
-                uint2 v = P.nd[node];
-                if (FPoly::type_of(v.y) == T_TRAPEZOID) continue;
-                const uint32_t ul = I.eul[e];
-                const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
-                const float2 Pu = sxy[up], Pl = sxy[lo];
-                do {
-                    bool both;
-                    const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
-                    if (both) {
-                        const uint32_t nw = atomicAdd(&I.ctr[0], 1u);
-                        if (nw >= I.cap) {
-                            I.ctr[1] = 1;
-                            break;
-                        }
-                        I.it_node[nw] = (uint16_t)(v.x >> 16);  // child2, searched after everything under child1
-                        I.it_edge[nw] = (uint16_t)e;
-                        I.it_next[nw] = I.it_next[it];
-                        I.it_next[it] = (uint16_t)nw;
-                    }
-                    node = next;
-                    v = P.nd[node];
-                } while (FPoly::type_of(v.y) != T_TRAPEZOID);
-                I.it_node[it] = (uint16_t)node;
-            }
+            for (uint32_t it = start + tid; it < end; it += T) advance_item(P, I, it);
             team_sync<W>();  // every append of this round is done
             start = end;
             end = min(I.ctr[0], I.cap);
@@ -798,7 +804,7 @@ __device__ void team_helper(const BatchArgs& a, uint32_t pi, unsigned char* ws, 
         const uint32_t cmd = ts->cmd;
         if (cmd == TEAM_STOP) break;
         if (cmd & TEAM_REFRESH) {
-            team_refresh<W>(P, loc, ts->n, (cmd & TEAM_ITEMS) != 0u, I, ts->arg0, threadIdx.x);
+            team_refresh<W>(P.sxy, P.nd, loc, ts->n, (cmd & TEAM_ITEMS) != 0u, I, ts->arg0, threadIdx.x);
             team_bar<W>();
         } else if (cmd == TEAM_LOAD) {
             const uint64_t p0 = a.first_point[pi] - a.point_base;
@@ -945,18 +951,69 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     uint32_t ur_edge = ur_offset;
     bool ok = true;
     for (uint32_t at = 0; at < n && ok; ++at) {  // :484-494
-        if (at % refresh_every == 0) {
+        if (W == 1) {
+            // Single warp: the refresh written out in place.  (Same loops as team_refresh<1>, but the n <= 64 kernel is
+            // measurably faster -- 3 % -- with this exact form; the compiler's register allocation differs.)
+            if (at % refresh_every == 0) {
+                // lane-parallel advance of every pending point's cached location (loc is in rank space)
+                for (uint32_t r = lane; r < n; r += 32) {
+                    const uint32_t cur = loc[r];
+                    if (cur != FNIL) loc[r] = (uint16_t)P.locate(r, sxy[r], cur);  // never FNIL: r is not inserted yet
+                }
+                if (use_items && (at % item_period == 0)) {
+                    // lane-parallel advance of every pending edge's search; new sibling items are handled in
+                    // the next round
+                    uint32_t start = 0, end = ctr[0];
+                    while (start < end) {
+                        for (uint32_t it = start + lane; it < end; it += 32) {
+                            const uint32_t e = it_edge[it];
+                            if (ehead[e] == FNIL) continue;  // edge already inserted
+                            uint32_t node = it_node[it];
+                            uint2 v = P.nd[node];
+                            if (FPoly::type_of(v.y) == T_TRAPEZOID) continue;
+                            const uint32_t ul = eul[e];
+                            const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
+                            const float2 Pu = sxy[up], Pl = sxy[lo];
+                            do {
+                                bool both;
+                                const uint32_t next = P.dfs_step(v, up, lo, Pu, Pl, &both);
+                                if (both) {
+                                    const uint32_t nw = atomicAdd(&ctr[0], 1u);
+                                    if (nw >= caps.item_cap) {
+                                        ctr[1] = 1;
+                                        break;
+                                    }
+                                    it_node[nw] = (uint16_t)(v.x >> 16);  // child2, searched after everything under child1
+                                    it_edge[nw] = (uint16_t)e;
+                                    it_next[nw] = it_next[it];
+                                    it_next[it] = (uint16_t)nw;
+                                }
+                                node = next;
+                                v = P.nd[node];
+                            } while (FPoly::type_of(v.y) != T_TRAPEZOID);
+                            it_node[it] = (uint16_t)node;
+                        }
+                        __syncwarp();
+                        start = end;
+                        end = min(ctr[0], caps.item_cap);
+                    }
+                    if (ctr[1]) {  // pool exhausted: the next tier redoes this polygon with the literal search
+                        P.requeue = true;
+                        break;
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (at % refresh_every == 0) {
             const bool do_items = use_items && (at % item_period == 0);
             const uint32_t items_end = do_items ? ctr[0] : 0u;
-            if (W > 1) {
-                if (lane == 0) {
-                    ts->cmd = TEAM_REFRESH | (do_items ? TEAM_ITEMS : 0u);
-                    ts->arg0 = items_end;
-                }
-                team_bar<W>();
+            if (lane == 0) {
+                ts->cmd = TEAM_REFRESH | (do_items ? TEAM_ITEMS : 0u);
+                ts->arg0 = items_end;
             }
-            team_refresh<W>(P, loc, n, do_items, I, items_end, lane);
-            team_sync<W>();
+            team_bar<W>();
+            team_refresh<W>(sxy, P.nd, loc, n, do_items, I, items_end, lane);
+            team_bar<W>();
             if (do_items && ctr[1]) {  // pool exhausted: the next tier redoes this polygon with the literal search
                 P.requeue = true;
                 break;
