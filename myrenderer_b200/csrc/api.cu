@@ -97,6 +97,11 @@ int mr_context_destroy(mr_context* ctx) {
     for (int i = 0; i < MR_NUM_SCRATCH; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned_mailbox) cudaFreeHost(ctx->pinned_mailbox);
+    for (int i = 0; i < MR_NUM_AUX; ++i) {
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MR_OK;

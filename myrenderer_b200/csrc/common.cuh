@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -10,6 +11,8 @@
 #include "../../include/myrenderer_b200.h"
 
 #define MR_NUM_SCRATCH 12
+
+constexpr int MR_NUM_AUX = 8;
 
 struct mr_context {
     int device = 0;
@@ -24,7 +27,22 @@ struct mr_context {
     size_t scratch_bytes[MR_NUM_SCRATCH] = {0};
     // small pinned mailbox for device->host scalars
     void* pinned_mailbox = nullptr;
+    // side streams for the polygon size classes' retry pass (independent, mostly empty kernels whose launch
+    // latencies then overlap); created on first use
+    cudaStream_t aux[MR_NUM_AUX] = {nullptr};
+    cudaEvent_t fork_ev = nullptr;
+    cudaEvent_t join_ev[MR_NUM_AUX] = {nullptr};
 };
+
+inline int mr_aux_streams(mr_context* ctx) {
+    if (ctx->fork_ev) return 0;
+    for (int i = 0; i < MR_NUM_AUX; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess) return -2;
+        if (cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming) != cudaSuccess) return -2;
+    }
+    if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess) return -2;
+    return 0;
+}
 
 inline int mr_fail(mr_context* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (ctx) {

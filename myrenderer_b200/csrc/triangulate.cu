@@ -25,15 +25,33 @@ namespace {
 
 constexpr uint32_t NIL = 0xFFFFu;
 enum : uint32_t { T_POINT = 0, T_SEGMENT = 1, T_TRAPEZOID = 2 };
-constexpr int NUM_CLASSES = 6;  // tiers 0..4: n <= 64,128,256,512,1024 (shared memory); 5: up to MR_MAX (global)
+constexpr int NUM_CLASSES = 9;  // classes 0..7: shared-memory workspaces (see class_nmax); 8: up to MR_MAX (global memory)
+constexpr int CLASS_SLOTS = 16; // header words reserved per per-class array
 constexpr int NBINS = MR_MAX_POLYGON_POINTS + 1;  // polygons are queued by exact size, largest first
 constexpr int MAX_WARPS_PER_BLOCK = 4;
 
-__host__ __device__ inline uint32_t class_nmax(int c) { return 64u << c; }
+// Largest polygon of shared-memory class c.  Powers of two, plus the intermediate sizes at which the smaller
+// workspace lets one or two more polygons fit an SM (the large classes are bound by polygons in flight:
+// 704 points -> 3 per SM instead of 2, 352 -> 6 instead of 4, 192 -> 11 instead of 8).
+__host__ __device__ inline uint32_t class_nmax(int c) {
+    switch (c) {
+        case 0: return 64u;
+        case 1: return 128u;
+        case 2: return 192u;
+        case 3: return 256u;
+        case 4: return 352u;
+        case 5: return 512u;
+        case 6: return 704u;
+        default: return 1024u;
+    }
+}
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
-// (measured on B200: 2/4/8 for the 256/512/1024-point classes; 8 warps in the 512 class or 4 in the 256 class lose
-// polygons in flight to the register file and are slower)
-inline int team_warps(int c) { return c == 4 ? 8 : (c == 3 ? 4 : (c == 2 ? 2 : 1)); }
+// (measured on B200: 2/3/4/6/8 warps for the 256/352/512/704/1024-point classes; 8 warps in the 512 class or 4 in the
+// 256 class lose polygons in flight to the register file and are slower)
+inline int team_warps(int c) {
+    const uint32_t nmax = class_nmax(c);
+    return nmax <= 128u ? 1 : nmax <= 256u ? 2 : nmax == 352u ? 3 : nmax == 512u ? 4 : nmax == 704u ? 6 : 8;
+}
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
     while (c < NUM_CLASSES - 1 && n > class_nmax(c)) ++c;
@@ -103,7 +121,7 @@ struct BatchArgs {
     const uint32_t* order;        // polygon ids grouped by class
     const uint32_t* class_begin;  // NUM_CLASSES: first position of the class in `order` (sorted by size, descending)
     const uint32_t* class_end;    // NUM_CLASSES
-    uint32_t* queue_head;         // [0,8): fast tier per class; [8,16): spec tier per class; [16,18): general
+    uint32_t* queue_head;         // [c]: first pass of class c; [NUM_CLASSES + c]: its spec tier; [2*NUM_CLASSES + which]: general
     uint32_t* spec_list;          // npoly, class c's overflow at class_begin[c]..
     uint32_t* spec_count;         // NUM_CLASSES
     uint32_t* general_list;       // npoly
@@ -1244,6 +1262,10 @@ __global__ void unirand_seed_batch_k(const uint64_t* __restrict__ first_point, u
 }  // namespace
 
 // ---- host side -------------------------------------------------------------------------------
+// header of the work-list memory (words)
+enum { HDR_CLASS_BEGIN = 0, HDR_CLASS_END = CLASS_SLOTS, HDR_QUEUE_HEAD = 2 * CLASS_SLOTS, HDR_SPEC_COUNT = 5 * CLASS_SLOTS,
+       HDR_GENERAL_COUNT = 6 * CLASS_SLOTS, HEADER_WORDS = 8 * CLASS_SLOTS };
+static_assert(NUM_CLASSES <= CLASS_SLOTS && 2 * NUM_CLASSES + 2 <= 3 * CLASS_SLOTS, "work-list header too small");
 enum { SLOT_XY = 0, SLOT_FP = 1, SLOT_FT = 2, SLOT_OP = 3, SLOT_VTX = 4, SLOT_BBOX = 5, SLOT_STATUS = 6, SLOT_NTRI = 7,
        SLOT_WORK = 8, SLOT_TIER1 = 9, SLOT_MISC = 10, SLOT_TIER1B = 11 };
 
@@ -1273,12 +1295,17 @@ int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev,
 int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]) {
     memset(out, 0, 8 * sizeof(uint32_t));
     if (!ctx->scratch[SLOT_WORK]) return MR_OK;
-    uint32_t hdr[64];
+    uint32_t hdr[HEADER_WORDS];
     MR_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->scratch[SLOT_WORK], sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream));
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int c = 0; c < NUM_CLASSES; ++c) out[c] = hdr[32 + c];  // spec_count
-    out[6] = hdr[40];                                              // general_count
-    out[7] = hdr[8 + NUM_CLASSES - 1] - hdr[NUM_CLASSES - 1];      // class_end - class_begin of the last class
+    // spec_count per internal class, folded into the documented size tiers <=64, 128, 256, 512, 1024
+    for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+        const uint32_t nmax = class_nmax(c);
+        const int tier = nmax <= 64u ? 0 : nmax <= 128u ? 1 : nmax <= 256u ? 2 : nmax <= 512u ? 3 : 4;
+        out[tier] += hdr[HDR_SPEC_COUNT + c];
+    }
+    out[6] = hdr[HDR_GENERAL_COUNT];
+    out[7] = hdr[HDR_CLASS_END + NUM_CLASSES - 1] - hdr[HDR_CLASS_BEGIN + NUM_CLASSES - 1];  // the > 1024 class
     return MR_OK;
 }
 
@@ -1288,16 +1315,16 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     if (npoly == 0) return MR_OK;
 
     // work-list memory: header | hist[NBINS] | cursor[NBINS] | order[npoly] | spec_list[npoly] | general_list[npoly]
-    const size_t header_words = 64;
+    const size_t header_words = HEADER_WORDS;
     void* work = nullptr;
     int rc = mr_scratch(ctx, SLOT_WORK, (header_words + 2 * (size_t)NBINS + 3 * (size_t)npoly) * 4, &work);
     if (rc) return rc;
     uint32_t* w = static_cast<uint32_t*>(work);
-    uint32_t* class_begin = w;        // NUM_CLASSES
-    uint32_t* class_end = w + 8;      // NUM_CLASSES
-    uint32_t* queue_head = w + 16;    // 2*NUM_CLASSES + 2
-    uint32_t* spec_count = w + 32;    // NUM_CLASSES
-    uint32_t* general_count = w + 40; // 1
+    uint32_t* class_begin = w + HDR_CLASS_BEGIN;      // NUM_CLASSES
+    uint32_t* class_end = w + HDR_CLASS_END;          // NUM_CLASSES
+    uint32_t* queue_head = w + HDR_QUEUE_HEAD;        // 2*NUM_CLASSES + 2
+    uint32_t* spec_count = w + HDR_SPEC_COUNT;        // NUM_CLASSES
+    uint32_t* general_count = w + HDR_GENERAL_COUNT;  // 1
     uint32_t* hist = w + header_words;
     uint32_t* cursor = hist + NBINS;
     uint32_t* order = cursor + NBINS;
@@ -1346,36 +1373,48 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     a.tier1_ws = nullptr;
     a.tier1_ws_stride = 0;
 
-    // fast path: per class, first with typical-case arenas, then the overflow with contract-cap arenas
+    // fast path: per class, first with typical-case arenas, then the overflow with contract-cap arenas.  The first pass
+    // runs class after class on the caller's stream (measured: running the classes concurrently costs the 1M-polygon
+    // batch 4 %, the large classes lose SM residency to the small ones).  The second pass is eight mostly empty
+    // kernels: each goes to its own side stream, so their launch latencies overlap; the caller's stream forks and
+    // joins around it.
+    static_assert(NUM_CLASSES - 1 <= MR_NUM_AUX, "one side stream per shared-memory class");
+    if (mr_aux_streams(ctx)) return mr_fail(ctx, MR_E_CUDA, "side streams");
     for (int spec = 0; spec < 2; ++spec) {
+        if (spec) MR_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
         for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+            cudaStream_t st = spec ? ctx->aux[c] : ctx->stream;
+            if (spec) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_ev, 0));
             const FCaps caps = fast_caps(c, spec != 0);
             const FLayout L = fast_layout(caps);
             const int team = spec ? 1 : team_warps(c);
             if (team > 1) {  // one polygon per block, `team` warps per polygon
                 const size_t smem = L.total;
                 if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = team == 2 ? triangulate_team_k<2> : (team == 4 ? triangulate_team_k<4> : triangulate_team_k<8>);
+                auto kern = team == 2 ? triangulate_team_k<2> : team == 3 ? triangulate_team_k<3> : team == 4 ? triangulate_team_k<4> : team == 6 ? triangulate_team_k<6> : triangulate_team_k<8>;
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
                 MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));
                 if (per_sm < 1) per_sm = 1;
-                kern<<<(unsigned)(ctx->sm_count * per_sm), team * 32, smem, ctx->stream>>>(a, c);
+                kern<<<(unsigned)(ctx->sm_count * per_sm), team * 32, smem, st>>>(a, c);
                 MR_LAUNCH_CHECK(ctx, "triangulate_team_k");
-                continue;
+            } else {
+                int wpb = MAX_WARPS_PER_BLOCK;
+                while (wpb > 1 && L.total * wpb > ctx->smem_optin / 2) wpb >>= 1;  // keep >= 2 blocks per SM when possible
+                const size_t smem = L.total * wpb;
+                if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
+                MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_fast_k, wpb * 32, smem));
+                if (per_sm < 1) per_sm = 1;
+                const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
+                triangulate_fast_k<<<grid, wpb * 32, smem, st>>>(a, c, spec);
+                MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");
             }
-            int wpb = MAX_WARPS_PER_BLOCK;
-            while (wpb > 1 && L.total * wpb > ctx->smem_optin / 2) wpb >>= 1;  // keep >= 2 blocks per SM when possible
-            const size_t smem = L.total * wpb;
-            if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-            MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_fast_k, wpb * 32, smem));
-            if (per_sm < 1) per_sm = 1;
-            const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
-            triangulate_fast_k<<<grid, wpb * 32, smem, ctx->stream>>>(a, c, spec);
-            MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");
+            if (spec) MR_CUDA(ctx, cudaEventRecord(ctx->join_ev[c], st));
         }
+        if (spec)
+            for (int c = 0; c < NUM_CLASSES - 1; ++c) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c], 0));
     }
     // general path: global-memory workspaces, one per warp of the grid
     for (int which = 0; which < 2; ++which) {
