@@ -46,11 +46,11 @@ __host__ __device__ inline uint32_t class_nmax(int c) {
     }
 }
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
-// (measured on B200: 2/3/4/6/8 warps for the 256/352/512/704/1024-point classes; 8 warps in the 512 class or 4 in the
-// 256 class lose polygons in flight to the register file and are slower)
+// (measured on B200: 3/4/6/8 warps for the 352/512/704/1024-point classes; up to 256 points independent warps are as
+// fast as teams of two; 8 warps in the 512 class lose polygons in flight to the register file)
 inline int team_warps(int c) {
     const uint32_t nmax = class_nmax(c);
-    return nmax <= 128u ? 1 : nmax <= 256u ? 2 : nmax == 352u ? 3 : nmax == 512u ? 4 : nmax == 704u ? 6 : 8;
+    return nmax <= 256u ? 1 : nmax == 352u ? 3 : nmax == 512u ? 4 : nmax == 704u ? 6 : 8;
 }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
@@ -1391,7 +1391,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             if (team > 1) {  // one polygon per block, `team` warps per polygon
                 const size_t smem = L.total;
                 if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = team == 2 ? triangulate_team_k<2> : team == 3 ? triangulate_team_k<3> : team == 4 ? triangulate_team_k<4> : team == 6 ? triangulate_team_k<6> : triangulate_team_k<8>;
+                auto kern = team == 3 ? triangulate_team_k<3> : team == 4 ? triangulate_team_k<4> : team == 6 ? triangulate_team_k<6> : triangulate_team_k<8>;
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
                 MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));
@@ -1399,14 +1399,21 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                 kern<<<(unsigned)(ctx->sm_count * per_sm), team * 32, smem, st>>>(a, c);
                 MR_LAUNCH_CHECK(ctx, "triangulate_team_k");
             } else {
-                int wpb = MAX_WARPS_PER_BLOCK;
-                while (wpb > 1 && L.total * wpb > ctx->smem_optin / 2) wpb >>= 1;  // keep >= 2 blocks per SM when possible
+                // independent warps, 4, 2 or 1 per block: whichever puts the most polygons on an SM (ties: larger blocks)
+                if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
+                MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)std::min<size_t>(L.total * MAX_WARPS_PER_BLOCK, ctx->smem_optin)));
+                int wpb = 1, per_sm = 1;
+                for (int w = MAX_WARPS_PER_BLOCK; w >= 1; w >>= 1) {
+                    if (L.total * w > ctx->smem_optin) continue;
+                    int b = 0;
+                    MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, triangulate_fast_k, w * 32, L.total * w));
+                    if (b * w > per_sm * wpb || (w == MAX_WARPS_PER_BLOCK && b >= 1)) {
+                        wpb = w;
+                        per_sm = b;
+                    }
+                }
                 const size_t smem = L.total * wpb;
-                if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int per_sm = 0;
-                MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, triangulate_fast_k, wpb * 32, smem));
-                if (per_sm < 1) per_sm = 1;
                 const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
                 triangulate_fast_k<<<grid, wpb * 32, smem, st>>>(a, c, spec);
                 MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");
