@@ -12,7 +12,7 @@
 
 #define MR_NUM_SCRATCH 12
 
-constexpr int MR_NUM_AUX = 8;
+constexpr int MR_NUM_AUX = 12;
 
 struct mr_context {
     int device = 0;

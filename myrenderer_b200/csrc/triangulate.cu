@@ -25,32 +25,34 @@ namespace {
 
 constexpr uint32_t NIL = 0xFFFFu;
 enum : uint32_t { T_POINT = 0, T_SEGMENT = 1, T_TRAPEZOID = 2 };
-constexpr int NUM_CLASSES = 9;  // classes 0..7: shared-memory workspaces (see class_nmax); 8: up to MR_MAX (global memory)
+constexpr int NUM_CLASSES = 11;  // classes 0..9: shared-memory workspaces (see class_nmax); 10: up to MR_MAX (global memory)
 constexpr int CLASS_SLOTS = 16; // header words reserved per per-class array
 constexpr int NBINS = MR_MAX_POLYGON_POINTS + 1;  // polygons are queued by exact size, largest first
 constexpr int MAX_WARPS_PER_BLOCK = 4;
 
-// Largest polygon of shared-memory class c.  Powers of two, plus the intermediate sizes at which the smaller
-// workspace lets one or two more polygons fit an SM (the large classes are bound by polygons in flight:
-// 704 points -> 3 per SM instead of 2, 352 -> 6 instead of 4, 192 -> 11 instead of 8).
+// Largest polygon of shared-memory class c.  Above 64 points a class is bound by the polygons whose workspaces
+// (~80 bytes per point, fast_layout) fit the SM's 228 KB, so the boundaries sit where one more polygon fits:
+// 1024 points -> 2 per SM, 960 -> 3, 712 -> 4, 568 -> 5, 464 -> 6, 344 -> 8, 256 -> 10, 192 -> 13, 128 -> 19.
 __host__ __device__ inline uint32_t class_nmax(int c) {
     switch (c) {
         case 0: return 64u;
         case 1: return 128u;
         case 2: return 192u;
         case 3: return 256u;
-        case 4: return 352u;
-        case 5: return 512u;
-        case 6: return 704u;
+        case 4: return 344u;
+        case 5: return 464u;
+        case 6: return 568u;
+        case 7: return 712u;
+        case 8: return 960u;
         default: return 1024u;
     }
 }
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
-// (measured on B200: 3/4/6/8 warps for the 352/512/704/1024-point classes; up to 256 points independent warps are as
-// fast as teams of two; 8 warps in the 512 class lose polygons in flight to the register file)
+// (measured on B200: 3/4/5/6/8 warps for the 464/568/712/960/1024-point classes; up to 344 points independent warps
+// are as fast as teams of two; too wide a team loses polygons in flight to the register file)
 inline int team_warps(int c) {
     const uint32_t nmax = class_nmax(c);
-    return nmax <= 256u ? 1 : nmax == 352u ? 3 : nmax == 512u ? 4 : nmax == 704u ? 6 : 8;
+    return nmax <= 344u ? 1 : nmax == 464u ? 3 : nmax == 568u ? 4 : nmax == 712u ? 5 : nmax == 960u ? 6 : 8;
 }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
@@ -1053,6 +1055,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
     const uint32_t count = spec ? a.spec_count[c] : (a.class_end[c] - begin);
     const uint32_t* list = spec ? a.spec_list : a.order;
     uint32_t* head = spec ? &a.queue_head[NUM_CLASSES + c] : &a.queue_head[c];
+    if (count == 0) return;  // empty class: no queue traffic
     for (;;) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(head, 1u);
@@ -1086,6 +1089,7 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
     const bool main_warp = threadIdx.x < 32u;
     const uint32_t begin = a.class_begin[c];
     const uint32_t count = a.class_end[c] - begin;
+    if (count == 0) return;  // empty class: no queue traffic
     for (;;) {
         if (threadIdx.x == 0) ts.qidx = atomicAdd(&a.queue_head[c], 1u);
         __syncthreads();
@@ -1375,9 +1379,9 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
 
     // fast path: per class, first with typical-case arenas, then the overflow with contract-cap arenas.  The first pass
     // runs class after class on the caller's stream (measured: running the classes concurrently costs the 1M-polygon
-    // batch 4 %, the large classes lose SM residency to the small ones).  The second pass is eight mostly empty
-    // kernels: each goes to its own side stream, so their launch latencies overlap; the caller's stream forks and
-    // joins around it.
+    // batch 4 %, the large classes lose SM residency to the small ones; splitting off only the n <= 64 class gains
+    // nothing).  The second pass is ten mostly empty kernels: each goes to its own side stream, so their launch
+    // latencies overlap; the caller's stream forks and joins around it.
     static_assert(NUM_CLASSES - 1 <= MR_NUM_AUX, "one side stream per shared-memory class");
     if (mr_aux_streams(ctx)) return mr_fail(ctx, MR_E_CUDA, "side streams");
     for (int spec = 0; spec < 2; ++spec) {
@@ -1391,7 +1395,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             if (team > 1) {  // one polygon per block, `team` warps per polygon
                 const size_t smem = L.total;
                 if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = team == 3 ? triangulate_team_k<3> : team == 4 ? triangulate_team_k<4> : team == 6 ? triangulate_team_k<6> : triangulate_team_k<8>;
+                auto kern = team == 3 ? triangulate_team_k<3> : team == 4 ? triangulate_team_k<4> : team == 5 ? triangulate_team_k<5> : team == 6 ? triangulate_team_k<6> : triangulate_team_k<8>;
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
                 MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));

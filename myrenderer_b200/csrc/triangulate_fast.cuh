@@ -55,15 +55,16 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
             k.stack_cap = 64u;  // the serial search hands over to the parallel one at 48 leaves (own output list)
             k.add_cap = 3u * k.nmax + 32u;
         } else {
-            k.node_cap = 6u * k.nmax + 16u;
+            // measured on convex input (n = 65..1024): nodes <= 4.82 n, items ever created <= 1.82 n (= the sum of the
+            // stack lengths: n initial items plus one per straddled point node), adds <= 1.4 n
+            k.node_cap = 5u * k.nmax + k.nmax / 4u + 16u;
             k.stack_cap = k.nmax + 32u;
             k.add_cap = 2u * k.nmax + 16u;
         }
         // conflict lists pay for themselves on larger polygons only (measured: 1.35-1.55x for n up to 1024,
-        // a small loss for n <= 64 where the per-edge polling overhead exceeds the search it saves)
-        // items are not recycled, so the pool must hold every item ever created (n initial + one per straddled
-        // point node met by a pending edge): ~3-4n on convex input; 4n+64 sent half of the 1024-gons to the retry tier
-        k.item_cap = c >= 1 ? 6u * k.nmax + 64u : 0u;  // the pool is reused by the mountain-phase arrays later
+        // a small loss for n <= 64 where the per-edge polling overhead exceeds the search it saves).
+        // Items are not recycled, so the pool must hold every item ever created.
+        k.item_cap = c >= 1 ? 2u * k.nmax + k.nmax / 2u + 64u : 0u;  // the pool is reused by the mountain-phase arrays later
     } else {
         k.item_cap = 0;  // measured: conflict lists slow the retry tier down (8.1 vs 6.1 ms on the 100k star batch)
         k.node_cap = MR_NODE_CAP(k.nmax);
@@ -92,16 +93,18 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     const size_t pool = o;
     L.add_pp = o;  o += align16((size_t)k.add_cap * 4);
     L.add_key = o; o += align16((size_t)k.add_cap * 4);
-    L.add_m = o;   o += align16((size_t)k.add_cap * 2);
-    L.mcount = o;  o += align16((size_t)k.add_cap * 4);
-    L.mstart = o;  o += align16((size_t)(k.add_cap + 1) * 2);
-    if (k.par_separate_out) {  // retry tier: room for the parallel search's items up to the contract stack cap
-        const size_t need = pool + 16 + align16((size_t)(k.stack_cap + 2u) * 4);
-        if (o < need) o = need;
-    }
-    const size_t mountain_end = o;
     L.it_node = L.it_next = L.it_edge = L.ehead = L.eul = L.ctr = 0;
     if (k.item_cap) {
+        // Conflict-list classes are bound by the polygons that fit an SM, so every array that can live in dead
+        // space does.  After the part-2 scan the node arena is dead; the finish phase lays its five u16 sort arrays
+        // (Gpos, cum, Gid, Gm, S; 2*add_cap entries each) over it.  add_m is last read while Gpos/Gid/Gm are
+        // written and S is not yet: it sits in S.  mcount is last used there too and cum is written after: it sits
+        // in cum.  mstart lives until the end; it takes rk+loc+stack (6n+64 bytes, all dead once the mountains
+        // are ranked -- efirst, which aliases loc, is last read before mstart is first written).
+        L.mcount = L.nodes + (size_t)k.add_cap * 4;   // = cum
+        L.add_m = L.nodes + (size_t)k.add_cap * 16;   // = S
+        L.mstart = L.rk;
+        const size_t mountain_end = o;
         o = pool;
         L.it_node = o; o += align16((size_t)k.item_cap * 2);
         L.it_next = o; o += align16((size_t)k.item_cap * 2);
@@ -110,6 +113,14 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
         L.eul = o;     o += align16((size_t)k.nmax * 4);
         L.ctr = o;     o += 16;
         if (o < mountain_end) o = mountain_end;
+    } else {
+        L.add_m = o;   o += align16((size_t)k.add_cap * 2);
+        L.mcount = o;  o += align16((size_t)k.add_cap * 4);
+        L.mstart = o;  o += align16((size_t)(k.add_cap + 1) * 2);
+        if (k.par_separate_out) {  // retry tier: room for the parallel search's items up to the contract stack cap
+            const size_t need = pool + 16 + align16((size_t)(k.stack_cap + 2u) * 4);
+            if (o < need) o = need;
+        }
     }
     L.efirst = L.loc;
     L.total = o;
@@ -950,7 +961,13 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     const bool ur_simple = ur_offset < n && ur_prime < n;
     uint32_t ur_edge = ur_offset;
     bool ok = true;
+#ifdef MR_DEBUG_ITEMS
+    uint32_t dbg_freed = 0, dbg_maxlive = 0;
+#endif
     for (uint32_t at = 0; at < n && ok; ++at) {  // :484-494
+#ifdef MR_DEBUG_ITEMS
+        if (use_items) dbg_maxlive = max(dbg_maxlive, ctr[0] - dbg_freed);
+#endif
         if (W == 1) {
             // Single warp: the refresh written out in place.  (Same loops as team_refresh<1>, but the n <= 64 kernel is
             // measurably faster -- 3 % -- with this exact form; the compiler's register allocation differs.)
@@ -1052,6 +1069,9 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             const float2 Pu = sxy[up], Pl = sxy[lo];
             uint32_t it = ehead[edge];
             while (it != FNIL && ok) {
+#ifdef MR_DEBUG_ITEMS
+                ++dbg_freed;
+#endif
                 uint32_t node = it_node[it];
                 uint32_t nxt = it_next[it];
                 for (;;) {
@@ -1098,6 +1118,10 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         ok = P.pass2(p1, up, lo, lane, 16u);  // pass 2: scan as written below 16 entries, REDUX arg-min above
         __syncwarp();
     }
+#ifdef MR_DEBUG_ITEMS
+    if (use_items && lane == 0 && (pi % 97u) == 0u)
+        printf("DBG n %u created %u maxlive %u nodes %u requeue %d\n", n, ctr[0], dbg_maxlive, P.nnodes, (int)P.requeue);
+#endif
     if (P.requeue) return F_REQUEUE_SPEC;
     if (!ok) {
         res->status = P.status | (sink.cap_vtx ? MR_POLY_UNDERFILL : 0u);
