@@ -1045,6 +1045,7 @@ __device__ __forceinline__ void write_result(const BatchArgs& a, uint32_t pi, co
 // ---- kernels ----------------------------------------------------------------------------------
 // Fast path, class c, shared-memory workspace.  spec == 0: the class's polygons with arenas sized for
 // the typical case; spec == 1: the polygons that outgrew those, with arenas at the contract caps.
+template <bool ITEMS>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(const BatchArgs a, int c, int spec) {
     extern __shared__ __align__(16) unsigned char smem[];
     const FCaps caps = fast_caps(c, spec != 0);
@@ -1063,7 +1064,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
         if (idx >= count) break;
         const uint32_t pi = list[begin + idx];
         Result r;
-        int rc = process_polygon_fast<1>(a, pi, ws, caps, L, &r, nullptr);
+        int rc = process_polygon_fast<1, ITEMS>(a, pi, ws, caps, L, &r, nullptr);
         if (rc == F_REQUEUE_SPEC && spec) rc = F_REQUEUE_GENERAL;  // the spec tier has no bigger shared-memory tier
         if (rc == F_DONE) {
             write_result(a, pi, r);
@@ -1098,7 +1099,7 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
         const uint32_t pi = a.order[begin + idx];
         if (main_warp) {
             Result r;
-            const int rc = process_polygon_fast<W>(a, pi, smem, caps, L, &r, &ts);
+            const int rc = process_polygon_fast<W, true>(a, pi, smem, caps, L, &r, &ts);
             if (lane == 0) ts.cmd = TEAM_STOP;
             team_bar<W>();
             if (rc == F_DONE) {
@@ -1405,13 +1406,14 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             } else {
                 // independent warps, 4, 2 or 1 per block: whichever puts the most polygons on an SM (ties: larger blocks)
                 if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                MR_CUDA(ctx, cudaFuncSetAttribute(triangulate_fast_k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                auto kern = caps.item_cap ? triangulate_fast_k<true> : triangulate_fast_k<false>;
+                MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)std::min<size_t>(L.total * MAX_WARPS_PER_BLOCK, ctx->smem_optin)));
                 int wpb = 1, per_sm = 1;
                 for (int w = MAX_WARPS_PER_BLOCK; w >= 1; w >>= 1) {
                     if (L.total * w > ctx->smem_optin) continue;
                     int b = 0;
-                    MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, triangulate_fast_k, w * 32, L.total * w));
+                    MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, w * 32, L.total * w));
                     if (b * w > per_sm * wpb || (w == MAX_WARPS_PER_BLOCK && b >= 1)) {
                         wpb = w;
                         per_sm = b;
@@ -1419,7 +1421,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                 }
                 const size_t smem = L.total * wpb;
                 const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
-                triangulate_fast_k<<<grid, wpb * 32, smem, st>>>(a, c, spec);
+                kern<<<grid, wpb * 32, smem, st>>>(a, c, spec);
                 MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");
             }
             if (spec) MR_CUDA(ctx, cudaEventRecord(ctx->join_ev[c], st));

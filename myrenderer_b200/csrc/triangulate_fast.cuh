@@ -829,7 +829,9 @@ __device__ void team_helper(const BatchArgs& a, uint32_t pi, unsigned char* ws, 
 }
 
 // All 32 lanes of the main warp call this.  Returns F_DONE with *res filled, or a requeue code.
-template <int W>
+// ITEMS: the class keeps conflict lists (caps.item_cap != 0); a compile-time switch so that the n <= 64 kernel and
+// the retry tiers do not carry the conflict-list code, nor the conflict-list classes the search from the root.
+template <int W, bool ITEMS>
 __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps,
                                     const FLayout L, Result* res, TeamShared* ts) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -908,7 +910,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     __syncwarp();
 
     // ---- conflict lists of the pending edges (items tier) ---------------------------------------------
-    const bool use_items = caps.item_cap != 0;
+    constexpr bool use_items = ITEMS;
 #ifndef MR_TEAM_LOC_DIV
 #define MR_TEAM_LOC_DIV 64u
 #endif
