@@ -1045,9 +1045,11 @@ __device__ __forceinline__ void write_result(const BatchArgs& a, uint32_t pi, co
 // ---- kernels ----------------------------------------------------------------------------------
 // Fast path, class c, shared-memory workspace.  spec == 0: the class's polygons with arenas sized for
 // the typical case; spec == 1: the polygons that outgrew those, with arenas at the contract caps.
-template <bool ITEMS>
-__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(const BatchArgs a, int c, int spec) {
+// CLASS0: the first pass of the n <= 64 class, with class and tier known at compile time (caps and layout fold to constants).
+template <bool ITEMS, bool CLASS0>
+__global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(const BatchArgs a, int c_arg, int spec_arg) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int c = CLASS0 ? 0 : c_arg, spec = CLASS0 ? 0 : spec_arg;
     const FCaps caps = fast_caps(c, spec != 0);
     const FLayout L = fast_layout(caps);
     unsigned char* ws = smem + (size_t)(threadIdx.x >> 5) * L.total;  // blockDim.x/32 warps per block
@@ -1406,7 +1408,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             } else {
                 // independent warps, 4, 2 or 1 per block: whichever puts the most polygons on an SM (ties: larger blocks)
                 if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = caps.item_cap ? triangulate_fast_k<true> : triangulate_fast_k<false>;
+                auto kern = caps.item_cap ? triangulate_fast_k<true, false> : (c == 0 && !spec) ? triangulate_fast_k<false, true> : triangulate_fast_k<false, false>;
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)std::min<size_t>(L.total * MAX_WARPS_PER_BLOCK, ctx->smem_optin)));
                 int wpb = 1, per_sm = 1;
