@@ -309,6 +309,8 @@ def main():
     ok_c = int((cstat == 0).sum().item())
     P.triangulate(job_p)  # leave the star batch's statuses in pstat for the report below
     ctx.sync()
+    tiers = (C.c_uint32 * 8)()
+    lib.mr_triangulate_tier_counts(ctx.handle, tiers)  # how the star batch was spread over the arena tiers
 
     # ---- end to end through the C ABI with pinned host buffers --------------------------------
     e2e = None
@@ -462,6 +464,8 @@ def main():
             "polygons_convex": {"value": polys_total / (g_ms_c * 1e-3), "unit": "polygons/s", "ms": g_ms_c,
                                 "status_ok_fraction": ok_c_total / polys_total,
                                 "note": "same sizes, convex (rotated ellipses): the family the reference triangulates correctly"},
+            "polygon_tiers": {"retried_with_contract_cap_arenas": int(sum(tiers[0:6])), "general_path": int(tiers[6]),
+                              "note": "rank 0's star batch; everything else ran in the first shared-memory pass"},
             "gpu_launches": launches_total,
             "wall_s_timed_region": wall,
             "clocks": clocks,

@@ -10,7 +10,7 @@
 #include <vector>
 #include "../../include/myrenderer_b200.h"
 
-#define MR_NUM_SCRATCH 12
+#define MR_NUM_SCRATCH 13
 
 constexpr int MR_NUM_AUX = 12;
 

@@ -130,6 +130,7 @@ struct BatchArgs {
     uint32_t* general_count;
     unsigned char* tier1_ws;
     size_t tier1_ws_stride;
+    unsigned char* par_ws;  // n <= 64 kernel: PAR_GL_BYTES of global scratch per warp of its grid
 };
 
 // ---- the per-polygon state machine ----------------------------------------------------------
@@ -1059,6 +1060,8 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
     const uint32_t* list = spec ? a.spec_list : a.order;
     uint32_t* head = spec ? &a.queue_head[NUM_CLASSES + c] : &a.queue_head[c];
     if (count == 0) return;  // empty class: no queue traffic
+    unsigned char* const par_gl =
+        CLASS0 && a.par_ws ? a.par_ws + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PAR_GL_BYTES : nullptr;
     for (;;) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(head, 1u);
@@ -1066,7 +1069,7 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(c
         if (idx >= count) break;
         const uint32_t pi = list[begin + idx];
         Result r;
-        int rc = process_polygon_fast<1, ITEMS>(a, pi, ws, caps, L, &r, nullptr);
+        int rc = process_polygon_fast<1, ITEMS>(a, pi, ws, caps, L, &r, nullptr, par_gl);
         if (rc == F_REQUEUE_SPEC && spec) rc = F_REQUEUE_GENERAL;  // the spec tier has no bigger shared-memory tier
         if (rc == F_DONE) {
             write_result(a, pi, r);
@@ -1274,7 +1277,7 @@ enum { HDR_CLASS_BEGIN = 0, HDR_CLASS_END = CLASS_SLOTS, HDR_QUEUE_HEAD = 2 * CL
        HDR_GENERAL_COUNT = 6 * CLASS_SLOTS, HEADER_WORDS = 8 * CLASS_SLOTS };
 static_assert(NUM_CLASSES <= CLASS_SLOTS && 2 * NUM_CLASSES + 2 <= 3 * CLASS_SLOTS, "work-list header too small");
 enum { SLOT_XY = 0, SLOT_FP = 1, SLOT_FT = 2, SLOT_OP = 3, SLOT_VTX = 4, SLOT_BBOX = 5, SLOT_STATUS = 6, SLOT_NTRI = 7,
-       SLOT_WORK = 8, SLOT_TIER1 = 9, SLOT_MISC = 10, SLOT_TIER1B = 11 };
+       SLOT_WORK = 8, SLOT_TIER1 = 9, SLOT_MISC = 10, SLOT_TIER1B = 11, SLOT_PAR = 12 };
 
 int mr_polygon_offsets_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly,
                             uint64_t* first_tri_dev) {
@@ -1379,6 +1382,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
     a.general_count = general_count;
     a.tier1_ws = nullptr;
     a.tier1_ws_stride = 0;
+    a.par_ws = nullptr;
 
     // fast path: per class, first with typical-case arenas, then the overflow with contract-cap arenas.  The first pass
     // runs class after class on the caller's stream (measured: running the classes concurrently costs the 1M-polygon
@@ -1394,6 +1398,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             if (spec) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_ev, 0));
             const FCaps caps = fast_caps(c, spec != 0);
             const FLayout L = fast_layout(caps);
+            if (!fast_layout_ok(caps, L)) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace layout is inconsistent");
             const int team = spec ? 1 : team_warps(c);
             if (team > 1) {  // one polygon per block, `team` warps per polygon
                 const size_t smem = L.total;
@@ -1422,6 +1427,12 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                     }
                 }
                 const size_t smem = L.total * wpb;
+                if (c == 0 && !spec) {  // global scratch of the parallel search, one slice per warp of the grid
+                    void* pw = nullptr;
+                    rc = mr_scratch(ctx, SLOT_PAR, (size_t)ctx->sm_count * per_sm * wpb * PAR_GL_BYTES, &pw);
+                    if (rc) return rc;
+                    a.par_ws = static_cast<unsigned char*>(pw);
+                }
                 const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
                 kern<<<grid, wpb * 32, smem, st>>>(a, c, spec);
                 MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");

@@ -113,19 +113,42 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
         L.eul = o;     o += align16((size_t)k.nmax * 4);
         L.ctr = o;     o += 16;
         if (o < mountain_end) o = mountain_end;
+    } else if (!k.par_separate_out) {
+        // n <= 64 class: the same overlays (there mstart takes rk+loc+cstack+stack = 8n bytes >= 2*(add_cap+1))
+        L.mcount = L.nodes + (size_t)k.add_cap * 4;   // = cum
+        L.add_m = L.nodes + (size_t)k.add_cap * 16;   // = S
+        L.mstart = L.rk;
+#ifndef MR_POOL0_MIN
+#define MR_POOL0_MIN 1792
+#endif
+        if (o < pool + MR_POOL0_MIN) o = pool + MR_POOL0_MIN;  // scratch of the parallel search (exploding searches)
     } else {
         L.add_m = o;   o += align16((size_t)k.add_cap * 2);
         L.mcount = o;  o += align16((size_t)k.add_cap * 4);
         L.mstart = o;  o += align16((size_t)(k.add_cap + 1) * 2);
-        if (k.par_separate_out) {  // retry tier: room for the parallel search's items up to the contract stack cap
-            const size_t need = pool + 16 + align16((size_t)(k.stack_cap + 2u) * 4);
-            if (o < need) o = need;
-        }
+        // retry tier: room for the parallel search's items up to the contract stack cap
+        const size_t need = pool + 16 + align16((size_t)(k.stack_cap + 2u) * 4);
+        if (o < need) o = need;
     }
     L.efirst = L.loc;
     L.total = o;
     return L;
 }
+
+// host-side check of the overlay assumptions above (called once per launch configuration)
+inline bool fast_layout_ok(const FCaps& k, const FLayout& L) {
+    if (k.par_separate_out) return true;  // retry tier: no overlays
+    const bool sort_fits = (size_t)k.add_cap * 20 <= (size_t)k.node_cap * 8;              // Gpos, cum, Gid, Gm, S over the node arena
+    const bool mstart_fits = L.rk + align16((size_t)(k.add_cap + 1) * 2) <= L.nodes;      // mstart over rk .. stack
+    const bool rank_fits = (size_t)k.nmax * 8 + (size_t)k.nmax * 2 * 8 <= (size_t)k.node_cap * 8 &&  // raw + keys (n2 <= 2n)
+                           (size_t)k.nmax * 2 * 2 <= (size_t)k.add_cap * 4;                // kidx over add_pp
+    return sort_fits && mstart_fits && rank_fits;
+}
+
+// per-warp global-memory scratch of the n <= 64 kernel's parallel search: items (node, next) and the output list,
+// PAR_GL_CAP entries each -- more than MR_STACK_CAP(64), so that overflowing it is the contract's MR_POLY_ARENA
+constexpr uint32_t PAR_GL_CAP = MR_STACK_CAP(64u) + 8u;
+constexpr size_t PAR_GL_BYTES = ((size_t)PAR_GL_CAP * 3u * 2u + 127u) & ~(size_t)127u;
 
 // outcome of the fast path besides a Result
 enum : int { F_DONE = 0, F_REQUEUE_SPEC = 1, F_REQUEUE_GENERAL = 2 };
@@ -833,7 +856,7 @@ __device__ void team_helper(const BatchArgs& a, uint32_t pi, unsigned char* ws, 
 // the retry tiers do not carry the conflict-list code, nor the conflict-list classes the search from the root.
 template <int W, bool ITEMS>
 __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps,
-                                    const FLayout L, Result* res, TeamShared* ts) {
+                                    const FLayout L, Result* res, TeamShared* ts, unsigned char* par_gl = nullptr) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint64_t p0 = a.first_point[pi] - a.point_base;
@@ -1111,7 +1134,17 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             P.stack = stack_home;
             const int sr = P.search_from_root(up, lo, par_cap ? 48u : 0xFFFFFFFFu);
             if (sr == 2) {
-                if (!P.search_parallel(up, lo, par_node, par_next, par_cap, par_out, par_out_cap, par_ctr, lane)) ok = false;
+                if (!P.search_parallel(up, lo, par_node, par_next, par_cap, par_out, par_out_cap, par_ctr, lane)) {
+                    ok = false;
+                    if (par_gl && P.requeue) {
+                        // The shared-memory scratch is sized for occupancy, not for the worst case: the (rare) search
+                        // that outgrows it is redone in this warp's global-memory scratch, which holds the contract cap
+                        // -- cheaper than sending the polygon to the retry launch, whose few polygons run alone on the GPU.
+                        P.requeue = false;
+                        uint16_t* g = reinterpret_cast<uint16_t*>(par_gl);
+                        ok = P.search_parallel(up, lo, g, g + PAR_GL_CAP, PAR_GL_CAP, g + 2u * PAR_GL_CAP, PAR_GL_CAP, par_ctr, lane) != 0;
+                    }
+                }
             } else if (sr == 0) {
                 ok = false;
             }
