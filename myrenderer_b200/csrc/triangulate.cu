@@ -50,7 +50,7 @@ __host__ __device__ inline uint32_t class_nmax(int c) {
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
 // (measured on B200: 3/4/5/6/8 warps for the 464/568/712/960/1024-point classes; up to 344 points independent warps
 // are as fast as teams of two; too wide a team loses polygons in flight to the register file)
-inline int team_warps(int c) {
+inline int team_warps(int c) {  // keep in step with the kernel tables in mr_triangulate_impl
     const uint32_t nmax = class_nmax(c);
     return nmax <= 344u ? 1 : nmax == 464u ? 3 : nmax == 568u ? 4 : nmax == 712u ? 5 : nmax == 960u ? 6 : 8;
 }
@@ -1046,11 +1046,13 @@ __device__ __forceinline__ void write_result(const BatchArgs& a, uint32_t pi, co
 // ---- kernels ----------------------------------------------------------------------------------
 // Fast path, class c, shared-memory workspace.  spec == 0: the class's polygons with arenas sized for
 // the typical case; spec == 1: the polygons that outgrew those, with arenas at the contract caps.
-// CLASS0: the first pass of the n <= 64 class, with class and tier known at compile time (caps and layout fold to constants).
-template <bool ITEMS, bool CLASS0>
+// CLS >= 0: the first pass of class CLS, with class and tier known at compile time (caps and layout fold to constants:
+// the n <= 64 kernel needs 64 registers instead of 96); CLS < 0: class and tier from the arguments (retry tiers).
+template <bool ITEMS, int CLS>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(const BatchArgs a, int c_arg, int spec_arg) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int c = CLASS0 ? 0 : c_arg, spec = CLASS0 ? 0 : spec_arg;
+    constexpr bool CLASS0 = CLS == 0;
+    const int c = CLS >= 0 ? CLS : c_arg, spec = CLS >= 0 ? 0 : spec_arg;
     const FCaps caps = fast_caps(c, spec != 0);
     const FLayout L = fast_layout(caps);
     unsigned char* ws = smem + (size_t)(threadIdx.x >> 5) * L.total;  // blockDim.x/32 warps per block
@@ -1403,7 +1405,15 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             if (team > 1) {  // one polygon per block, `team` warps per polygon
                 const size_t smem = L.total;
                 if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = team == 3 ? triangulate_team_k<3> : team == 4 ? triangulate_team_k<4> : team == 5 ? triangulate_team_k<5> : team == 6 ? triangulate_team_k<6> : triangulate_team_k<8>;
+                void (*kern)(const BatchArgs, int) = nullptr;  // one instantiation per team width: see team_warps
+                switch (team) {
+                    case 3: kern = triangulate_team_k<3>; break;
+                    case 4: kern = triangulate_team_k<4>; break;
+                    case 5: kern = triangulate_team_k<5>; break;
+                    case 6: kern = triangulate_team_k<6>; break;
+                    case 8: kern = triangulate_team_k<8>; break;
+                }
+                if (!kern) return mr_fail(ctx, MR_E_CUDA, "no team kernel of this width");
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
                 MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));
@@ -1413,7 +1423,16 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
             } else {
                 // independent warps, 4, 2 or 1 per block: whichever puts the most polygons on an SM (ties: larger blocks)
                 if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                auto kern = caps.item_cap ? triangulate_fast_k<true, false> : (c == 0 && !spec) ? triangulate_fast_k<false, true> : triangulate_fast_k<false, false>;
+                void (*kern)(const BatchArgs, int, int) = triangulate_fast_k<false, -1>;  // retry tiers
+                if (!spec) {
+                    switch (c) {
+                        case 0: kern = triangulate_fast_k<false, 0>; break;
+                        // (compile-time class constants were measured for the other kernels too: no gain for the
+                        // single-warp conflict-list classes, 8 % slower for the team kernels)
+                        case 1: case 2: case 3: case 4: kern = triangulate_fast_k<true, -1>; break;
+                        default: return mr_fail(ctx, MR_E_CUDA, "no single-warp kernel for this class");
+                    }
+                }
                 MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)std::min<size_t>(L.total * MAX_WARPS_PER_BLOCK, ctx->smem_optin)));
                 int wpb = 1, per_sm = 1;

@@ -48,9 +48,9 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
     k.par_separate_out = spec;
     if (!spec) {
         if (c == 0) {
-            // tier 0 is register-limited to 5 blocks/SM, which leaves ~11 KB of shared memory per warp:
-            // spend it on contract-cap node arenas and a deep stack so that almost no polygon needs the
-            // retry tier (whose separate launch is tail-bound)
+            // contract-cap node arena, so that no polygon of this class needs the retry tier for nodes (its separate
+            // launch is tail-bound); 7.4 KB per warp = 28 warps per SM, past the point where the kernel is
+            // issue-bound (smaller arenas were measured: no gain)
             k.node_cap = MR_NODE_CAP(k.nmax);
             k.stack_cap = 64u;  // the serial search hands over to the parallel one at 48 leaves (own output list)
             k.add_cap = 3u * k.nmax + 32u;
@@ -118,10 +118,6 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
         L.mcount = L.nodes + (size_t)k.add_cap * 4;   // = cum
         L.add_m = L.nodes + (size_t)k.add_cap * 16;   // = S
         L.mstart = L.rk;
-#ifndef MR_POOL0_MIN
-#define MR_POOL0_MIN 1792
-#endif
-        if (o < pool + MR_POOL0_MIN) o = pool + MR_POOL0_MIN;  // scratch of the parallel search (exploding searches)
     } else {
         L.add_m = o;   o += align16((size_t)k.add_cap * 2);
         L.mcount = o;  o += align16((size_t)k.add_cap * 4);
