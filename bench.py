@@ -249,6 +249,23 @@ def main():
     cstat = torch.empty(npoly, dtype=torch.int32, device=dev)
     job_c = P.job(cxy, fp_d, npoly, vtx_out=pvtx, first_tri=ft_d, bbox_out=pbbox, status_out=cstat, ntri_out=pntri,
                   seed=SEED_POLY, poly_index0=pa, point_base=int(fp[0]))
+    # third polygon workload: a bounded sample of BASELINE config 5 (sizes log-uniform 8..1024, convex) per GPU
+    LARGE_PER_GPU = 50_000
+    fpl_all = np.zeros(LARGE_PER_GPU * world + 1, dtype=np.uint64)
+    lib.mr_synth_polygon_sizes(0x5EED0005, 0, LARGE_PER_GPU * world, 8, 1024, 1, fpl_all.ctypes.data)
+    lranges = (C.c_uint32 * (world + 1))()
+    lib.mr_polygon_partition(fpl_all.ctypes.data, LARGE_PER_GPU * world, world, lranges)
+    la, lb = lranges[rank], lranges[rank + 1]
+    fpl = np.ascontiguousarray(fpl_all[la:lb + 1])
+    ftl = mr.polygon_offsets_host(fpl)
+    nl, nl_pts = lb - la, int(fpl[-1] - fpl[0])
+    lxy, _ = ellipse_batch(fpl - fpl[0], 0xC5 + la, device=dev)
+    fpl_d = torch.from_numpy(fpl.view(np.int64)).to(dev)
+    ftl_d = torch.from_numpy(ftl.view(np.int64)).to(dev)
+    lvtx = torch.empty(int(ftl[-1]) * 3 * STRIDE, dtype=torch.uint8, device=dev)
+    lstat = torch.empty(nl, dtype=torch.int32, device=dev)
+    job_l = P.job(lxy, fpl_d, nl, vtx_out=lvtx, first_tri=ftl_d, status_out=lstat, seed=0x5EED0005, poly_index0=la,
+                  point_base=int(fpl[0]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 2x L2
     ctx.sync()
 
@@ -307,6 +324,20 @@ def main():
     barrier()
     ms_c = sum(x.elapsed_time(y) for x, y in tc) / len(tc)
     ok_c = int((cstat == 0).sum().item())
+    # ---- large-polygon sample, same protocol -----------------------------------------------------------
+    P.triangulate(job_l)
+    barrier()
+    tl = []
+    for _ in range(max(3, min(args.steps, 5))):
+        a_, b_ = ev(), ev()
+        a_.record()
+        P.triangulate(job_l)
+        b_.record()
+        flush.zero_()
+        tl.append((a_, b_))
+    barrier()
+    ms_l = sum(x.elapsed_time(y) for x, y in tl) / len(tl)
+    ok_l = int((lstat == 0).sum().item())
     P.triangulate(job_p)  # leave the star batch's statuses in pstat for the report below
     ctx.sync()
     tiers = (C.c_uint32 * 8)()
@@ -431,6 +462,8 @@ def main():
     ok_total = reduce_sum(int((pstat == 0).sum().item()))
     g_ms_c = reduce_max(ms_c)
     ok_c_total = reduce_sum(ok_c)
+    g_ms_l = reduce_max(ms_l)
+    ok_l_total, nl_total, nl_pts_total = reduce_sum(ok_l), reduce_sum(nl), reduce_sum(nl_pts)
     if gather is not None and "ms" in gather:
         gather["ms"] = reduce_max(gather["ms"])
 
@@ -464,6 +497,11 @@ def main():
             "polygons_convex": {"value": polys_total / (g_ms_c * 1e-3), "unit": "polygons/s", "ms": g_ms_c,
                                 "status_ok_fraction": ok_c_total / polys_total,
                                 "note": "same sizes, convex (rotated ellipses): the family the reference triangulates correctly"},
+            "polygons_large": {"value": nl_total / (g_ms_l * 1e-3), "unit": "polygons/s", "ms": g_ms_l,
+                               "mpoints_per_s": nl_pts_total / (g_ms_l * 1e-3) / 1e6, "polygons": int(nl_total),
+                               "status_ok_fraction": ok_l_total / nl_total,
+                               "note": "sample of BASELINE config 5: sizes log-uniform 8..1024 (mean 209 points), convex; "
+                                       "the full 1M-polygon run is scripts/bench_configs45.py"},
             "polygon_tiers": {"retried_with_contract_cap_arenas": int(sum(tiers[0:6])), "general_path": int(tiers[6]),
                               "note": "rank 0's star batch; everything else ran in the first shared-memory pass"},
             "gpu_launches": launches_total,
