@@ -1048,6 +1048,8 @@ __device__ __forceinline__ void write_result(const BatchArgs& a, uint32_t pi, co
 // the typical case; spec == 1: the polygons that outgrew those, with arenas at the contract caps.
 // CLS >= 0: the first pass of class CLS, with class and tier known at compile time (caps and layout fold to constants:
 // the n <= 64 kernel needs 64 registers instead of 96); CLS < 0: class and tier from the arguments (retry tiers).
+// (No minimum-blocks hint: ptxas picks 72 registers for the n <= 64 instantiation on its own; forcing 64, 80 or 96
+// through __launch_bounds__ was measured 15-35 % slower.)
 template <bool ITEMS, int CLS>
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_fast_k(const BatchArgs a, int c_arg, int spec_arg) {
     extern __shared__ __align__(16) unsigned char smem[];

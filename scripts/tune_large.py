@@ -1,4 +1,5 @@
-"""Timing of the polygon kernel on large polygons (convex ellipses; `log`: sizes log-uniform 8..1024, `big`: 512..1024)."""
+"""Timing of the polygon kernel on convex ellipses; `log`: sizes log-uniform 8..1024, `big`: 512..1024, `small`: 8..64
+(the bench's convex batch).  Also the target of the ncu captures in profiles/."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -17,7 +18,8 @@ def ellipses(fp, seed):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "log"
 npoly = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
-fp = O.synth_polygon_sizes(0x5EED0005, npoly, 8, 1024, 1) if which == "log" else O.synth_polygon_sizes(1, npoly, 512, 1024, 0)
+fp = (O.synth_polygon_sizes(0x5EED0005, npoly, 8, 1024, 1) if which == "log" else
+      O.synth_polygon_sizes(0x5EED0003, npoly, 8, 64, 0) if which == "small" else O.synth_polygon_sizes(1, npoly, 512, 1024, 0))
 xy = ellipses(fp, 3)
 ctx = mr.Context(0); P = mr.Polygon(ctx)
 for tune in ("default",):
