@@ -158,7 +158,19 @@ def run_reference_arm(args):
                          "note": "CPU = C restatement of the Zig source (oracle/), not the Zig binary"},
         "e2e": {"value": val, "unit": "Mverts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
 
 
 def workload_name(world: int) -> str:
@@ -181,6 +193,11 @@ def main():
                     help="N>1: also time building the terrain bands straight into rank 0's buffer over NVLink (IPC peer stores)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -536,7 +553,7 @@ def main():
                 "single_thread": {"terrain_mverts_per_s": cpu1["terrain_mverts_per_s"],
                                   "polygons_per_s": cpu1["polygons_per_s"], "sample": cpu1["sample"]},
                 "note": "CPU = C restatement of the Zig source (oracle/), prints removed; not the Zig binary"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

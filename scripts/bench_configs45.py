@@ -24,6 +24,9 @@ import myrenderer_b200 as mr
 from myrenderer_b200 import sharding
 from myrenderer_b200.workloads import ellipse_batch
 
+sys.stdout.flush()
+_OUT = os.dup(1)  # stdout carries only the JSON: library banners (NCCL version, ...) go to stderr
+os.dup2(2, 1)
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -162,7 +165,7 @@ if world > 1:
     release(gp)
 out["config5_polygons_1m"] = res5
 if rank == 0:
-    print(json.dumps(out, indent=1))
+    os.write(_OUT, (json.dumps(out, indent=1) + "\n").encode())
 if world > 1:
     dist.destroy_process_group()
 ctx.close()
