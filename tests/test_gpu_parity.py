@@ -353,6 +353,40 @@ def test_convex_and_large_polygons(ctx, oracle):
     assert (ref["status"] == 0).all(), "the reference algorithm handles convex polygons"
 
 
+def _convex(n, rng):
+    th = 2 * np.pi * (np.arange(n) + 0.8 * rng.random(n) - 0.4) / n
+    a, b, ph = 40 + 50 * rng.random(), 40 + 50 * rng.random(), rng.random() * 6.28
+    x, y = a * np.cos(th), b * np.sin(th)
+    return np.stack([100 + np.cos(ph) * x - np.sin(ph) * y, 100 + np.sin(ph) * x + np.cos(ph) * y], 1)
+
+
+def test_size_class_boundaries_convex_and_star(ctx, oracle):
+    """Every size class of the kernel (n <= 64, 128, 192, 256, 344, 464, 568, 712, 960, 1024, then global memory) at
+    its largest size and one past it; several polygons per size so that the persistent warps / warp teams run
+    their queue loop, and explicit unirand pairs as well as seeded ones."""
+    import myrenderer_b200 as mr
+
+    rng = np.random.default_rng(11)
+    sizes = []
+    for top in (64, 128, 192, 256, 344, 464, 568, 712, 960, 1024):
+        sizes += [top, top + 1] * 3
+    xy = np.concatenate([_convex(n, rng) for n in sizes]).astype(np.float32)
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=21)
+    assert (ref["status"] == 0).all()
+    tc = (C.c_uint32 * 8)()
+    ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
+    assert sum(tc[0:7]) == 0, list(tc)            # convex input: everything in the first shared-memory pass
+    assert tc[7] == 3                              # the three 1025-gons ride in the global-memory class
+    # explicit (offset, prime) pairs, incl. prime 1 and the largest table prime below n
+    ops = np.array([[1 + (i * 7) % (n - 1), 1 if i % 2 else 3] for i, n in enumerate(sizes)], dtype=np.uint32)
+    _check_batch(ctx, oracle, xy, fp, offset_prime=ops)
+    # star-shaped polygons of the same sizes: the reference algorithm fails on many of them (overflow, underfill,
+    # null unwrap, arena caps); status and bytes must still agree
+    sxy = oracle.synth_polygons(77, fp)
+    _check_batch(ctx, oracle, sxy, fp, seed=77)
+
+
 def test_skewed_sizes_loguniform(ctx, oracle):
     """Config 5 shape at reduced count: log-uniform sizes 8..1024, star-shaped (mostly failing in the
     reference algorithm -> exercises arena caps and re-queueing to the global-memory tier)."""
