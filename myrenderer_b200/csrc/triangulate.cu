@@ -1205,8 +1205,20 @@ __global__ void __launch_bounds__(1024) size_scan_k(const uint32_t* __restrict__
 
 __global__ void size_scatter_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npoly; i += gridDim.x * blockDim.x)
-        order[atomicAdd(&cursor[size_bin(first_point[i + 1] - first_point[i])], 1u)] = i;
+    // warp-aggregated: one atomic per distinct size per warp (a batch of small polygons has only a few dozen sizes)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t step = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < npoly; i0 += step) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < npoly;
+        const uint32_t bin = valid ? size_bin(first_point[i + 1] - first_point[i]) : 0xFFFFFFFFu;
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, bin);
+        const uint32_t leader = __ffs(same) - 1u;
+        uint32_t base = 0;
+        if (valid && lane == leader) base = atomicAdd(&cursor[bin], (uint32_t)__popc(same));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (valid) order[base + __popc(same & ((1u << lane) - 1u))] = i;
+    }
 }
 
 __global__ void polygon_offsets_k(const uint64_t* __restrict__ first_point, uint32_t npoly,
