@@ -482,6 +482,22 @@ __device__ __forceinline__ bool is_acute(const float2* pts, uint32_t point, uint
     return fabsf(__fsub_rn(a, b)) < __uint_as_float(0x40490fdbu);
 }
 
+// atan2f(dy, dx) certainly lies in [0, pi - 7e-7]: the vector points into the upper half-plane (or along +x) and makes
+// an angle of more than 1e-6 with the negative x axis.  (atan2f's error is an ulp or two, 2.4e-7 near pi.)
+__device__ __forceinline__ bool angle_clear_of_pi(float dy, float dx) {
+    return (dy > 0.0f && (dx >= 0.0f || dy > __fmul_rn(1e-6f, -dx))) || (dy == 0.0f && dx > 0.0f);
+}
+// Same value as is_acute.  When both angles are certainly in [0, pi - 7e-7], |a - b| <= max(a, b) < (f32)pi without
+// evaluating them -- the case of every triangle of a sorted mountain except a centre that sees a neighbour
+// within 1e-6 rad of the negative x axis, which takes the exact evaluation.
+__device__ __forceinline__ bool is_acute_shortcut(const float2* pts, uint32_t point, uint32_t axis1, uint32_t axis2) {
+    const float2 P = pts[point], A1 = pts[axis1], A2 = pts[axis2];
+    if (angle_clear_of_pi(__fsub_rn(P.y, A1.y), __fsub_rn(P.x, A1.x)) &&
+        angle_clear_of_pi(__fsub_rn(P.y, A2.y), __fsub_rn(P.x, A2.x)))
+        return true;
+    return is_acute(pts, point, axis1, axis2);
+}
+
 // emit order of Triangulation.zig:405-422; returns ids packed, count in *cnt (3, or 1 when an
 // axis equals the centre -- cannot happen after the equality checks, kept for fidelity)
 __device__ __forceinline__ void triangle_order(uint32_t point, uint32_t axis1, uint32_t axis2, uint32_t out[3],

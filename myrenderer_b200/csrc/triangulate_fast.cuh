@@ -689,7 +689,7 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
                 if (g >= s + 2u) {
                     const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
                     valid = (c != a1) && (c != a2);
-                    if (valid && !is_acute(sxy, c, a1, a2)) all_acute = false;
+                    if (valid && !is_acute_shortcut(sxy, c, a1, a2)) all_acute = false;
                 }
             }
             const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
@@ -710,7 +710,7 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
             if (g >= s + 2u) {
                 const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
                 valid = (c != a1) && (c != a2);
-                if (valid && !is_acute(sxy, c, a1, a2)) all_acute = false;
+                if (valid && !is_acute_shortcut(sxy, c, a1, a2)) all_acute = false;
             }
             cum[g] = valid ? 1u : 0u;
         }

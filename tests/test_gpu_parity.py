@@ -420,6 +420,37 @@ def test_edge_cases(ctx, oracle):
     assert ref["status"][4] == 2 and ref["status"][5] == 2
 
 
+def test_acute_test_near_the_negative_x_axis(ctx, oracle):
+    """push_triangle_if_acute (Triangulation.zig:398-425) compares two atan2 values with pi; the fast path only evaluates
+    atan2 when a difference vector comes within 1e-6 rad of the negative x axis.  Thin triangles whose lowest vertex sees
+    a neighbour at slopes 0, denormal, 1e-9 .. 1e-4 exercise both sides of that shortcut, at several magnitudes."""
+    rng = np.random.default_rng(3)
+    polys = []
+    for scale in (1.0, 1e-3, 1e10, 3e-20):
+        for slope in (0.0, 1e-45, 5e-41, 1e-38, 1e-12, 1e-9, 3e-8, 1e-7, 5e-7, 9e-7, 1.1e-6, 2e-6, 1e-5, 1e-4):
+            for k in range(6):
+                w = scale * (1.0 + rng.random())
+                y_far = w * slope * (1.0 + 0.5 * rng.random())          # far point barely above/at the near point's level
+                y_mid = 0.5 * y_far * rng.random()
+                tri = np.array([[0.0, 0.0], [2.0 * w, y_far], [w, y_mid]])
+                if k % 2:
+                    tri = tri[::-1].copy()
+                if k % 3 == 0:
+                    tri[:, 0] = -tri[:, 0]
+                polys.append(tri)
+    # quadrilaterals with a nearly flat bottom chain as well
+    for slope in (1e-41, 1e-9, 1e-7, 1e-6, 1e-5):
+        for w in (1.0, 1e8):
+            polys.append(np.array([[0.0, 0.0], [w, w * slope], [2 * w, 2.5 * w * slope], [w, -w]]))
+            polys.append(np.array([[0.0, 0.0], [w, -w], [2 * w, 2.5 * w * slope], [w, w * slope]]))
+    xy = np.concatenate(polys).astype(np.float32)
+    fp = np.concatenate([[0], np.cumsum([len(q) for q in polys])]).astype(np.uint64)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=4)
+    # every polygon must have taken a definite path: statuses agree (checked above) and the batch contains both
+    # polygons that emit their full n-2 triangles and ones that do not
+    assert (ref["ntri"] > 0).any()
+
+
 def test_too_large_polygon(ctx, oracle):
     n = 4097
     th = 2 * np.pi * np.arange(n) / n
