@@ -945,8 +945,11 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
 #ifndef MR_TEAM_ITEM_MULT
 #define MR_TEAM_ITEM_MULT 4u
 #endif
+    // the caches are refreshed every refresh_every edges, the conflict lists every item_mult-th refresh (single warp:
+    // measured best of 1/2/4/8 on n <= 1024); countdowns instead of `at % period` (a run-time modulo per edge)
     const uint32_t refresh_every = W > 1 ? (n + MR_TEAM_LOC_DIV - 1u) / MR_TEAM_LOC_DIV : (n + 63u) / 64u;
-    const uint32_t item_period = (W > 1 ? MR_TEAM_ITEM_MULT : 4u) * refresh_every;  // single warp: measured best of 1/2/4/8 on n <= 1024
+    const uint32_t item_mult = W > 1 ? MR_TEAM_ITEM_MULT : 4u;
+    uint32_t refresh_wait = 0, item_wait = 0;
     const FItems I = fast_items(ws, L, caps);
     uint16_t *const it_node = I.it_node, *const it_next = I.it_next, *const it_edge = I.it_edge, *const ehead = I.ehead;
     uint32_t *const eul = I.eul, *const ctr = I.ctr;
@@ -998,16 +1001,20 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
 #ifdef MR_DEBUG_ITEMS
         if (use_items) dbg_maxlive = max(dbg_maxlive, ctr[0] - dbg_freed);
 #endif
+        const bool refresh_now = refresh_wait == 0u;
+        refresh_wait = refresh_now ? refresh_every - 1u : refresh_wait - 1u;
+        const bool items_now = use_items && refresh_now && item_wait == 0u;
+        if (refresh_now) item_wait = item_wait == 0u ? item_mult - 1u : item_wait - 1u;
         if (W == 1) {
             // Single warp: the refresh written out in place.  (Same loops as team_refresh<1>, but the n <= 64 kernel is
             // measurably faster -- 3 % -- with this exact form; the compiler's register allocation differs.)
-            if (at % refresh_every == 0) {
+            if (refresh_now) {
                 // lane-parallel advance of every pending point's cached location (loc is in rank space)
                 for (uint32_t r = lane; r < n; r += 32) {
                     const uint32_t cur = loc[r];
                     if (cur != FNIL) loc[r] = (uint16_t)P.locate(r, sxy[r], cur);  // never FNIL: r is not inserted yet
                 }
-                if (use_items && (at % item_period == 0)) {
+                if (items_now) {
                     // lane-parallel advance of every pending edge's search; new sibling items are handled in
                     // the next round
                     uint32_t start = 0, end = ctr[0];
@@ -1051,8 +1058,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
                 }
                 __syncwarp();
             }
-        } else if (at % refresh_every == 0) {
-            const bool do_items = use_items && (at % item_period == 0);
+        } else if (refresh_now) {
+            const bool do_items = items_now;
             const uint32_t items_end = do_items ? ctr[0] : 0u;
             if (lane == 0) {
                 ts->cmd = TEAM_REFRESH | (do_items ? TEAM_ITEMS : 0u);
