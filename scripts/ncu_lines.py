@@ -38,7 +38,7 @@ tot, ts = sum(inst.values()) or 1, sum(samp.values()) or 1
 print(f"total warp-instructions {tot}, stall samples {ts}")
 args = sys.argv[1:]
 topn = int(args[0]) if args and args[0].isdigit() else 30
-for spec in [a for a in args if "=" in a]:
+for spec in [a for a in args if "=" in a and ":" in a]:
     rng, label = spec.split("=")
     f, lohi = rng.split(":")
     lo, hi = (int(x) for x in lohi.split("-"))
