@@ -947,7 +947,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
 #endif
     // the caches are refreshed every refresh_every edges, the conflict lists every item_mult-th refresh (single warp:
     // measured best of 1/2/4/8 on n <= 1024); countdowns instead of `at % period` (a run-time modulo per edge)
-    const uint32_t refresh_every = W > 1 ? (n + MR_TEAM_LOC_DIV - 1u) / MR_TEAM_LOC_DIV : (n + 63u) / 64u;
+    // (without conflict lists -- n <= 64 and the retry tiers -- every 4th edge measured best of 1/2/3/4/6/8/16)
+    const uint32_t refresh_every = W > 1 ? (n + MR_TEAM_LOC_DIV - 1u) / MR_TEAM_LOC_DIV : (!ITEMS ? 4u * ((n + 63u) / 64u) : (n + 63u) / 64u);
     const uint32_t item_mult = W > 1 ? MR_TEAM_ITEM_MULT : 4u;
     uint32_t refresh_wait = 0, item_wait = 0;
     const FItems I = fast_items(ws, L, caps);
