@@ -152,7 +152,10 @@ enum : int { F_DONE = 0, F_REQUEUE_SPEC = 1, F_REQUEUE_GENERAL = 2 };
 struct FPoly {
     const float2* sxy;
     uint2* nd;
-    uint16_t* stack;
+    uint16_t* stack;   // node_stack of the segment being inserted: always shared memory ...
+    uint16_t* gstack;  // ... unless this is non-null: the (rare) list that only fitted the global-memory scratch.
+                       // Two members so that the compiler keeps `stack` in the shared address space (LDS/STS, no
+                       // generic-pointer arithmetic on the hot path).
     uint16_t* cstack;
     uint32_t nnodes, nstack, status;
     uint32_t tier_node_cap, tier_stack_cap, spec_node_cap, spec_stack_cap;
@@ -278,6 +281,7 @@ struct FPoly {
     // items until every item sits on a trapezoid; the list is then copied into node_stack.
     //   it_node/it_next: item arrays (cap entries), out: node_stack to fill (out_cap entries), ctr: shared
     //   word.  Returns 1 done, 0 failure (status/requeue set).
+    template <bool GLOBAL>
     __device__ int search_parallel(uint32_t up, uint32_t lo, uint16_t* it_node, uint16_t* it_next, uint32_t cap,
                                    uint16_t* out, uint32_t out_cap, uint32_t* ctr, uint32_t lane) {
         const float2 Pu = sxy[up], Pl = sxy[lo];
@@ -338,13 +342,18 @@ struct FPoly {
             it = it_next[it];
         }
         __syncwarp();
-        stack = out;
+        if (GLOBAL) gstack = out; else stack = out;
         nstack = total;
         return 1;
     }
 
     // pass 2 of add_segment (:316-395) on node_stack; p1 is the rank id of the edge's first point
     __device__ bool pass2(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
+        return gstack ? pass2_on<true>(p1, up, lo, lane, serial_below) : pass2_on<false>(p1, up, lo, lane, serial_below);
+    }
+    template <bool GLOBAL>
+    __device__ bool pass2_on(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
+        uint16_t* const stk = GLOBAL ? gstack : stack;
         // The two open trapezoids live in registers until they are closed.
         uint32_t left = alloc();
         if (left == FNIL) return false;
@@ -360,7 +369,7 @@ struct FPoly {
             uint32_t base_index = 0, low = lo;
             if (nstack <= serial_below) {  // short stack: the scan as written
                 for (uint32_t i = 0; i < nstack; ++i) {
-                    const uint32_t np = nd[stack[i]].y >> 16;
+                    const uint32_t np = nd[stk[i]].y >> 16;
                     if (np == FNIL) {  // :330 `.?`
                         status |= MR_POLY_NULL_UNWRAP;
                         return false;
@@ -374,7 +383,7 @@ struct FPoly {
                 uint32_t best = 0xFFFFFFFFu;
                 bool null_p2 = false;
                 for (uint32_t i = lane; i < nstack; i += 32) {
-                    const uint32_t np = nd[stack[i]].y >> 16;
+                    const uint32_t np = nd[stk[i]].y >> 16;
                     null_p2 = null_p2 || (np == FNIL);
                     best = min(best, (np << 16) | i);
                 }
@@ -388,7 +397,7 @@ struct FPoly {
                     base_index = best & 0xFFFFu;
                 }
             }
-            const uint32_t base_id = stack[base_index];
+            const uint32_t base_id = stk[base_index];
             const uint32_t bch = nd[base_id].x;  // :347-360
             lx = (lx & 0xFFFF0000u) | (bch & 0xFFFFu);
             rx = (rx & 0x0000FFFFu) | (bch & 0xFFFF0000u);
@@ -417,7 +426,7 @@ struct FPoly {
                 rx = fresh;
                 ry = low | (T_TRAPEZOID << 14) | (FNIL << 16);
             }
-            stack[base_index] = stack[nstack - 1];  // :394
+            stk[base_index] = stk[nstack - 1];  // :394
             --nstack;
             __syncwarp();
         }
@@ -926,6 +935,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
     P.stack = reinterpret_cast<uint16_t*>(ws + L.stack);
     P.cstack = reinterpret_cast<uint16_t*>(ws + L.cstack);
+    P.gstack = nullptr;
     P.nnodes = 1;  // :479 root trapezoid
     P.nstack = 0;
     P.status = MR_POLY_OK;
@@ -1145,9 +1155,10 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             // redone as a parallel frontier expansion (items + output list live in the mountain arrays,
             // unused during part 1)
             P.stack = stack_home;
+            P.gstack = nullptr;
             const int sr = P.search_from_root(up, lo, par_cap ? 48u : 0xFFFFFFFFu);
             if (sr == 2) {
-                if (!P.search_parallel(up, lo, par_node, par_next, par_cap, par_out, par_out_cap, par_ctr, lane)) {
+                if (!P.search_parallel<false>(up, lo, par_node, par_next, par_cap, par_out, par_out_cap, par_ctr, lane)) {
                     ok = false;
                     if (par_gl && P.requeue) {
                         // The shared-memory scratch is sized for occupancy, not for the worst case: the (rare) search
@@ -1155,7 +1166,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
                         // -- cheaper than sending the polygon to the retry launch, whose few polygons run alone on the GPU.
                         P.requeue = false;
                         uint16_t* g = reinterpret_cast<uint16_t*>(par_gl);
-                        ok = P.search_parallel(up, lo, g, g + PAR_GL_CAP, PAR_GL_CAP, g + 2u * PAR_GL_CAP, PAR_GL_CAP, par_ctr, lane) != 0;
+                        ok = P.search_parallel<true>(up, lo, g, g + PAR_GL_CAP, PAR_GL_CAP, g + 2u * PAR_GL_CAP, PAR_GL_CAP, par_ctr, lane) != 0;
                     }
                 }
             } else if (sr == 0) {
