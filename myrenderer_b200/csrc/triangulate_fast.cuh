@@ -258,13 +258,19 @@ struct FPoly {
         uint32_t base = 0, ncr = 0;
         nstack = 0;
         for (;;) {      // loop1 :231
-            for (;;) {  // loop :232
-                const uint2 v = nd[base];
+            uint2 v = nd[base];
+            for (;;) {  // loop :232, with runs of point nodes in a loop of their own
+                while (type_of(v.y) == T_POINT) {
+                    const uint32_t pa = v.y & FNIL14;
+                    const bool first = pa > up;
+                    if (first && pa < lo) cstack[ncr++] = (uint16_t)base;
+                    base = first ? (v.x & 0xFFFFu) : (v.x >> 16);
+                    v = nd[base];
+                }
                 if (type_of(v.y) == T_TRAPEZOID) break;
                 bool both;
-                const uint32_t next = dfs_step(v, up, lo, Pu, Pl, &both);
-                if (both) cstack[ncr++] = (uint16_t)base;
-                base = next;
+                base = dfs_step(v, up, lo, Pu, Pl, &both);  // a segment node: never a breadcrumb
+                v = nd[base];
             }
             if (!push(base)) return 0;  // :302
             if (ncr == 0) break;        // :306-313
