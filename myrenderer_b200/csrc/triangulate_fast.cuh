@@ -48,12 +48,12 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
     k.par_separate_out = spec;
     if (!spec) {
         if (c == 0) {
-            // contract-cap node arena, so that no polygon of this class needs the retry tier for nodes (its separate
-            // launch is tail-bound); 7.4 KB per warp = 28 warps per SM, past the point where the kernel is
-            // issue-bound (smaller arenas were measured: no gain)
-            k.node_cap = MR_NODE_CAP(k.nmax);
+            // 7n nodes and 2.75n adds (the contract caps are 8n+64 and unbounded): no polygon of the benchmark's star
+            // batch outgrows them, and the 6.1 KB workspace lets the register file, not shared memory, set the
+            // occupancy (32 warps per SM at 64 registers; measured +3.5 % over contract-cap arenas at 28 warps)
+            k.node_cap = 7u * k.nmax;
             k.stack_cap = 64u;  // the serial search hands over to the parallel one at 48 leaves (own output list)
-            k.add_cap = 3u * k.nmax + 32u;
+            k.add_cap = 2u * k.nmax + (3u * k.nmax) / 4u;
         } else {
             // measured on convex input (n = 65..1024): nodes <= 4.82 n, items ever created <= 1.82 n (= the sum of the
             // stack lengths: n initial items plus one per straddled point node), adds <= 1.4 n
