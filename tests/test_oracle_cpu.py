@@ -151,6 +151,36 @@ def test_not_acute_corner_exists(oracle):
     assert r["stats"]["not_acute"] >= 1
 
 
+def test_acute_shortcut_condition_is_sound(oracle):
+    """The fast path skips atan2 in push_triangle_if_acute (Triangulation.zig:398-425) when both difference vectors
+    satisfy  dy > 0 and (dx >= 0 or dy > 1e-6 * -dx),  or  dy == 0 and dx > 0  (triangulate.cu: angle_clear_of_pi).
+    Its claim, checked here against the musl-exact atan2f of the oracle: such a vector's angle lies in
+    [0, (f32)pi - 5e-7], so |a - b| <= max(a, b) < (f32)pi and the comparison is decided without evaluating it."""
+    rng = np.random.default_rng(12)
+    pi32 = float(np.float32(math.pi))
+    worst = 0.0
+    samples = []
+    for mag in (1e-30, 1e-10, 1e-3, 1.0, 37.5, 1e6, 1e20, 1e35):
+        for ratio in (1.0000001e-6, 1.001e-6, 1.5e-6, 1e-5, 1e-3, 0.5, 1.0, 3.0, 1e3, 1e6):
+            for _ in range(40):
+                dx = -mag * (1.0 + rng.random())
+                dy = abs(dx) * ratio * (1.0 + 1e-3 * rng.random())
+                samples.append((dy, dx))
+        for _ in range(200):  # dx >= 0 branch, incl. dx = 0 and tiny dy
+            samples.append((mag * rng.random() + 1e-45, mag * rng.random() * (rng.random() > 0.2)))
+        samples.append((0.0, mag))  # dy == 0 and dx > 0
+    for dy, dx in samples:
+        with np.errstate(over="ignore"):  # 1e35 * 1e6 -> inf is a legitimate sample (atan2 = pi/2)
+            dy32, dx32 = np.float32(dy), np.float32(dx)
+        clear = (dy32 > 0 and (dx32 >= 0 or dy32 > np.float32(1e-6) * -dx32)) or (dy32 == 0 and dx32 > 0)
+        if not clear:
+            continue
+        a = oracle.atan2f(float(dy32), float(dx32))
+        assert 0.0 <= a <= pi32 - 5e-7, (dy, dx, a)
+        worst = max(worst, a)
+    assert worst > 3.14159  # the sample does reach the neighbourhood of the threshold
+
+
 # ---- unirand ------------------------------------------------------------------------------------
 PRIMES = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 101, 103,
           107, 109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193, 197, 199, 211, 223,
