@@ -31,28 +31,28 @@ constexpr int NBINS = MR_MAX_POLYGON_POINTS + 1;  // polygons are queued by exac
 constexpr int MAX_WARPS_PER_BLOCK = 4;
 
 // Largest polygon of shared-memory class c.  Above 64 points a class is bound by the polygons whose workspaces
-// (~80 bytes per point, fast_layout) fit the SM's 228 KB, so the boundaries sit where one more polygon fits:
-// 1024 points -> 2 per SM, 960 -> 3, 712 -> 4, 568 -> 5, 464 -> 6, 344 -> 8, 256 -> 10, 192 -> 13, 128 -> 19.
+// (~73 bytes per point, fast_layout) fit the SM's 228 KB, so the boundaries sit where one more polygon fits:
+// 1024 points -> 3 per SM, 768 -> 4, 608 -> 5, 504 -> 6, 368 -> 8, 288 -> 10, 216 -> 13, 168 -> 16, 128 -> 20.
 __host__ __device__ inline uint32_t class_nmax(int c) {
     switch (c) {
         case 0: return 64u;
         case 1: return 128u;
-        case 2: return 192u;
-        case 3: return 256u;
-        case 4: return 344u;
-        case 5: return 464u;
-        case 6: return 568u;
-        case 7: return 712u;
-        case 8: return 960u;
+        case 2: return 168u;
+        case 3: return 216u;
+        case 4: return 288u;
+        case 5: return 368u;
+        case 6: return 504u;
+        case 7: return 608u;
+        case 8: return 768u;
         default: return 1024u;
     }
 }
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
-// (measured on B200: 3/4/5/6/8 warps for the 464/568/712/960/1024-point classes; up to 344 points independent warps
-// are as fast as teams of two; too wide a team loses polygons in flight to the register file)
+// (3/4/6/8 warps for the 504/608/768/1024-point classes -- at most 24 warps of 80 registers per SM; up to 368 points
+// independent warps measured as fast as teams of two; too wide a team loses polygons in flight to the register file)
 inline int team_warps(int c) {  // keep in step with the kernel tables in mr_triangulate_impl
     const uint32_t nmax = class_nmax(c);
-    return nmax <= 344u ? 1 : nmax == 464u ? 3 : nmax == 568u ? 4 : nmax == 712u ? 5 : nmax == 960u ? 6 : 8;
+    return nmax <= 368u ? 1 : nmax == 504u ? 3 : nmax == 608u ? 4 : nmax == 768u ? 6 : 8;
 }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
@@ -1439,7 +1439,6 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                 switch (team) {
                     case 3: kern = triangulate_team_k<3>; break;
                     case 4: kern = triangulate_team_k<4>; break;
-                    case 5: kern = triangulate_team_k<5>; break;
                     case 6: kern = triangulate_team_k<6>; break;
                     case 8: kern = triangulate_team_k<8>; break;
                 }
@@ -1459,7 +1458,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                         case 0: kern = triangulate_fast_k<false, 0>; break;
                         // (compile-time class constants were measured for the other kernels too: no gain for the
                         // single-warp conflict-list classes, 8 % slower for the team kernels)
-                        case 1: case 2: case 3: case 4: kern = triangulate_fast_k<true, -1>; break;
+                        case 1: case 2: case 3: case 4: case 5: kern = triangulate_fast_k<true, -1>; break;
                         default: return mr_fail(ctx, MR_E_CUDA, "no single-warp kernel for this class");
                     }
                 }

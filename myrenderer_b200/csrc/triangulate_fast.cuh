@@ -76,13 +76,13 @@ __host__ __device__ inline FCaps fast_caps(int c, bool spec) {
 
 struct FLayout {
     size_t sxy, orig, rk, loc, cstack, stack, nodes, add_pp, add_key, add_m, mcount, mstart, efirst, total;
-    size_t it_node, it_next, it_edge, ehead, eul, ctr;  // items tier only
+    size_t it_node, it_next, it_edge, ehead, ctr;  // items tier only
 };
 __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     FLayout L;
     size_t o = 0;
     L.sxy = o;     o += align16((size_t)k.nmax * 8);
-    L.orig = o;    o += align16((size_t)k.nmax * 2);
+    L.orig = o;    o += k.item_cap ? 0 : align16((size_t)k.nmax * 2);  // conflict-list classes: see below
     L.rk = o;      o += align16((size_t)k.nmax * 2);
     L.loc = o;     o += align16((size_t)k.nmax * 2);
     L.cstack = o;  o += k.item_cap ? 0 : align16((size_t)k.nmax * 2);  // only the search from the root uses it
@@ -93,24 +93,26 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     const size_t pool = o;
     L.add_pp = o;  o += align16((size_t)k.add_cap * 4);
     L.add_key = o; o += align16((size_t)k.add_cap * 4);
-    L.it_node = L.it_next = L.it_edge = L.ehead = L.eul = L.ctr = 0;
+    L.it_node = L.it_next = L.it_edge = L.ehead = L.ctr = 0;
     if (k.item_cap) {
         // Conflict-list classes are bound by the polygons that fit an SM, so every array that can live in dead
         // space does.  After the part-2 scan the node arena is dead; the finish phase lays its five u16 sort arrays
         // (Gpos, cum, Gid, Gm, S; 2*add_cap entries each) over it.  add_m is last read while Gpos/Gid/Gm are
         // written and S is not yet: it sits in S.  mcount is last used there too and cum is written after: it sits
-        // in cum.  mstart lives until the end; it takes rk+loc+stack (6n+64 bytes, all dead once the mountains
+        // in cum.  mstart lives until the end; it takes rk+loc (+ a few bytes of stack; all dead once the mountains
         // are ranked -- efirst, which aliases loc, is last read before mstart is first written).
         L.mcount = L.nodes + (size_t)k.add_cap * 4;   // = cum
         L.add_m = L.nodes + (size_t)k.add_cap * 16;   // = S
         L.mstart = L.rk;
+        // orig (rank -> original id) is only read in part 2: it is rebuilt from rk after the trapezoidation, into the
+        // node_stack's space behind mstart
+        L.orig = L.rk + align16((size_t)(k.add_cap + 1) * 2);
         const size_t mountain_end = o;
         o = pool;
         L.it_node = o; o += align16((size_t)k.item_cap * 2);
         L.it_next = o; o += align16((size_t)k.item_cap * 2);
         L.it_edge = o; o += align16((size_t)k.item_cap * 2);
         L.ehead = o;   o += align16((size_t)k.nmax * 2);
-        L.eul = o;     o += align16((size_t)k.nmax * 4);
         L.ctr = o;     o += 16;
         if (o < mountain_end) o = mountain_end;
     } else if (!k.par_separate_out) {
@@ -135,7 +137,8 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
 inline bool fast_layout_ok(const FCaps& k, const FLayout& L) {
     if (k.par_separate_out) return true;  // retry tier: no overlays
     const bool sort_fits = (size_t)k.add_cap * 20 <= (size_t)k.node_cap * 8;              // Gpos, cum, Gid, Gm, S over the node arena
-    const bool mstart_fits = L.rk + align16((size_t)(k.add_cap + 1) * 2) <= L.nodes;      // mstart over rk .. stack
+    const bool mstart_fits = k.item_cap ? (L.orig + (size_t)k.nmax * 2 <= L.nodes)          // mstart, then orig, over rk .. stack
+                                        : (L.rk + align16((size_t)(k.add_cap + 1) * 2) <= L.nodes);
     const bool rank_fits = (size_t)k.nmax * 8 + (size_t)k.nmax * 2 * 8 <= (size_t)k.node_cap * 8 &&  // raw + keys (n2 <= 2n)
                            (size_t)k.nmax * 2 * 2 <= (size_t)k.add_cap * 4;                // kidx over add_pp
     return sort_fits && mstart_fits && rank_fits;
@@ -480,20 +483,21 @@ __device__ __forceinline__ void team_sync() {
 
 struct FItems {
     uint16_t *it_node, *it_next, *it_edge, *ehead;
-    uint32_t *eul, *ctr;
+    const uint16_t* rk;  // rank of original point i: edge e runs from rk[e] to rk[e+1 mod n]
+    uint32_t* ctr;
     uint32_t cap;
 };
 
 // One pending item of the conflict lists: continue its walk until it sits on a trapezoid; a straddled point node
 // links a sibling item right behind it (handled by a later round).
-__device__ __forceinline__ void advance_item(const FPoly& P, const FItems& I, uint32_t it) {
+__device__ __forceinline__ void advance_item(const FPoly& P, const FItems& I, uint32_t it, uint32_t n) {
     const uint32_t e = I.it_edge[it];
     if (I.ehead[e] == FNIL) return;  // edge already inserted
     uint32_t node = I.it_node[it];
     uint2 v = P.nd[node];
     if (FPoly::type_of(v.y) == T_TRAPEZOID) return;
-    const uint32_t ul = I.eul[e];
-    const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
+    const uint32_t pa = I.rk[e], pb = I.rk[e + 1u == n ? 0u : e + 1u];
+    const uint32_t up = min(pa, pb), lo = max(pa, pb);  // (upper, lower)  :218-224
     const float2 Pu = P.sxy[up], Pl = P.sxy[lo];
     do {
         bool both;
@@ -533,7 +537,7 @@ __device__ __forceinline__ void team_refresh(const float2* sxy, uint2* nd, uint1
         // (read by the main warp before the team started, so every warp runs the same rounds)
         uint32_t start = 0, end = items_end;
         while (start < end) {
-            for (uint32_t it = start + tid; it < end; it += T) advance_item(P, I, it);
+            for (uint32_t it = start + tid; it < end; it += T) advance_item(P, I, it, n);
             team_sync<W>();  // every append of this round is done
             start = end;
             end = min(I.ctr[0], I.cap);
@@ -838,7 +842,7 @@ __device__ __forceinline__ FItems fast_items(unsigned char* ws, const FLayout& L
     I.it_next = reinterpret_cast<uint16_t*>(ws + L.it_next);
     I.it_edge = reinterpret_cast<uint16_t*>(ws + L.it_edge);
     I.ehead = reinterpret_cast<uint16_t*>(ws + L.ehead);
-    I.eul = reinterpret_cast<uint32_t*>(ws + L.eul);
+    I.rk = reinterpret_cast<const uint16_t*>(ws + L.rk);
     I.ctr = reinterpret_cast<uint32_t*>(ws + L.ctr);  // [0] items allocated, [1] pool overflow flag
     I.cap = caps.item_cap;
     return I;
@@ -969,11 +973,9 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     uint32_t refresh_wait = 0, item_wait = 0;
     const FItems I = fast_items(ws, L, caps);
     uint16_t *const it_node = I.it_node, *const it_next = I.it_next, *const it_edge = I.it_edge, *const ehead = I.ehead;
-    uint32_t *const eul = I.eul, *const ctr = I.ctr;
+    uint32_t* const ctr = I.ctr;
     if (use_items) {
         for (uint32_t e = lane; e < n; e += 32) {  // every edge starts with one item at the root
-            const uint32_t pa = rk[e], pb = rk[e + 1u == n ? 0u : e + 1u];
-            eul[e] = min(pa, pb) | (max(pa, pb) << 16);  // (upper, lower)  :218-224
             it_node[e] = 0;
             it_next[e] = (uint16_t)FNIL;
             it_edge[e] = (uint16_t)e;
@@ -1042,8 +1044,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
                             uint32_t node = it_node[it];
                             uint2 v = P.nd[node];
                             if (FPoly::type_of(v.y) == T_TRAPEZOID) continue;
-                            const uint32_t ul = eul[e];
-                            const uint32_t up = ul & 0xFFFFu, lo = ul >> 16;
+                            const uint32_t ra = rk[e], rb = rk[e + 1u == n ? 0u : e + 1u];
+                            const uint32_t up = min(ra, rb), lo = max(ra, rb);  // (upper, lower)  :218-224
                             const float2 Pu = sxy[up], Pl = sxy[lo];
                             do {
                                 bool both;
@@ -1192,6 +1194,12 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         res->status = P.status | (sink.cap_vtx ? MR_POLY_UNDERFILL : 0u);
         sink.zero(0, sink.cap_vtx, lane);
         return F_DONE;
+    }
+
+    if (ITEMS) {
+        // rank -> original id, needed from here on: rebuilt behind mstart's place in the dead node_stack (fast_layout)
+        for (uint32_t i = lane; i < n; i += 32) orig[rk[i]] = (uint16_t)i;
+        __syncwarp();
     }
 
     // ---- part 2: inside trapezoids -> adds, in node id order (:510-540) ---------------------------

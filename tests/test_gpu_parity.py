@@ -361,14 +361,14 @@ def _convex(n, rng):
 
 
 def test_size_class_boundaries_convex_and_star(ctx, oracle):
-    """Every size class of the kernel (n <= 64, 128, 192, 256, 344, 464, 568, 712, 960, 1024, then global memory) at
+    """Every size class of the kernel (n <= 64, 128, 168, 216, 288, 368, 504, 608, 768, 1024, then global memory) at
     its largest size and one past it; several polygons per size so that the persistent warps / warp teams run
     their queue loop, and explicit unirand pairs as well as seeded ones."""
     import myrenderer_b200 as mr
 
     rng = np.random.default_rng(11)
     sizes = []
-    for top in (64, 128, 192, 256, 344, 464, 568, 712, 960, 1024):
+    for top in (64, 128, 168, 216, 288, 368, 504, 608, 768, 1024):
         sizes += [top, top + 1] * 3
     xy = np.concatenate([_convex(n, rng) for n in sizes]).astype(np.float32)
     fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
