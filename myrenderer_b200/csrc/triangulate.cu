@@ -48,11 +48,11 @@ __host__ __device__ inline uint32_t class_nmax(int c) {
     }
 }
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
-// (3/4/6/8 warps for the 504/608/768/1024-point classes -- at most 24 warps of 80 registers per SM; up to 368 points
-// independent warps measured as fast as teams of two; too wide a team loses polygons in flight to the register file)
+// (3/4/4/6/8 warps for the 368/504/608/768/1024-point classes -- at most 24 warps of 80 registers per SM; up to 288
+// points independent warps; too wide a team loses polygons in flight to the register file)
 inline int team_warps(int c) {  // keep in step with the kernel tables in mr_triangulate_impl
     const uint32_t nmax = class_nmax(c);
-    return nmax <= 368u ? 1 : nmax == 504u ? 3 : nmax == 608u ? 4 : nmax == 768u ? 6 : 8;
+    return nmax <= 288u ? 1 : nmax == 368u ? 3 : nmax <= 608u ? 4 : nmax == 768u ? 6 : 8;
 }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
@@ -1458,7 +1458,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                         case 0: kern = triangulate_fast_k<false, 0>; break;
                         // (compile-time class constants were measured for the other kernels too: no gain for the
                         // single-warp conflict-list classes, 8 % slower for the team kernels)
-                        case 1: case 2: case 3: case 4: case 5: kern = triangulate_fast_k<true, -1>; break;
+                        case 1: case 2: case 3: case 4: case 5: kern = triangulate_fast_k<true, -1>; break;  // (class 5 only when it is not a team class)
                         default: return mr_fail(ctx, MR_E_CUDA, "no single-warp kernel for this class");
                     }
                 }
