@@ -273,6 +273,22 @@ int mr_synth_polygon_sizes(uint64_t seed, uint64_t poly_index0, uint32_t npoly, 
  * radius 20..90.  xy_out holds first_point[npoly]-first_point[0] points. */
 int mr_synth_polygons(mr_context* ctx, uint64_t seed, uint64_t poly_index0,
                       const uint64_t* first_point, uint32_t npoly, float* xy_out);
+/* The same with a choice of family.  All families are simple polygons with positive shoelace area in
+ * raw (x,y) inside [0,200]^2, vertex k of polygon i drawn from the counter hash keyed by (seed, i, k):
+ *   MR_FAMILY_STAR     star-shaped about (100,100), radius 20..90 (= mr_synth_polygons).  Strongly
+ *                      non-convex; the reference algorithm fails on most of them above ~30 points.
+ *   MR_FAMILY_ELLIPSE  convex: jittered points of a randomly rotated ellipse (semi-axes 40..90).
+ *   MR_FAMILY_ZIPPER   non-convex, y-monotone: the right chain walks down the even levels and the
+ *                      left chain back up the odd levels of n strictly increasing jittered y levels,
+ *                      x free inside each chain's half -- jagged on both sides, but no edge contains
+ *                      a non-adjacent edge vertically, which is the precondition of the reference's
+ *                      segment-search defect (Triangulation.zig:275-286):
+ *                      the reference triangulates every member correctly for every edge order. */
+#define MR_FAMILY_STAR 0
+#define MR_FAMILY_ELLIPSE 1
+#define MR_FAMILY_ZIPPER 2
+int mr_synth_polygons_family(mr_context* ctx, int family, uint64_t seed, uint64_t poly_index0,
+                             const uint64_t* first_point, uint32_t npoly, float* xy_out);
 
 /* ---- multi-GPU plumbing (one process per GPU) ------------------------------ */
 #define MR_IPC_HANDLE_BYTES 64

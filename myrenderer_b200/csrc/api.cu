@@ -14,7 +14,7 @@ int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev,
                                uint64_t poly_index0, uint32_t* out_dev);
 int mr_synth_heightmap_u16_impl(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t row0, uint32_t rows,
                                 uint16_t* out_dev);
-int mr_synth_polygons_impl(mr_context* ctx, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point_dev,
+int mr_synth_polygons_impl(mr_context* ctx, int family, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point_dev,
                            uint32_t npoly, float* xy_dev);
 
 namespace {
@@ -545,7 +545,14 @@ int mr_synth_heightmap_u16(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t 
 
 int mr_synth_polygons(mr_context* ctx, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
                       uint32_t npoly, float* xy_out) {
+    return mr_synth_polygons_family(ctx, MR_FAMILY_STAR, seed, poly_index0, first_point, npoly, xy_out);
+}
+
+int mr_synth_polygons_family(mr_context* ctx, int family, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
+                             uint32_t npoly, float* xy_out) {
     if (!ctx || !first_point || !xy_out) return MR_E_BADARG;
+    if (family != MR_FAMILY_STAR && family != MR_FAMILY_ELLIPSE && family != MR_FAMILY_ZIPPER)
+        return mr_fail(ctx, MR_E_BADARG, "synth_polygons: unknown family");
     MR_CUDA(ctx, cudaSetDevice(ctx->device));
     const void* dfp = nullptr;
     int rc = mr_stage_in(ctx, 1, first_point, (size_t)(npoly + 1) * 8, &dfp);
@@ -559,7 +566,7 @@ int mr_synth_polygons(mr_context* ctx, uint64_t seed, uint64_t poly_index0, cons
     }
     rc = mr_stage_out(ctx, 0, xy_out, bytes, &dout, &st);
     if (rc) return rc;
-    rc = mr_synth_polygons_impl(ctx, seed, poly_index0, static_cast<const uint64_t*>(dfp), npoly, static_cast<float*>(dout));
+    rc = mr_synth_polygons_impl(ctx, family, seed, poly_index0, static_cast<const uint64_t*>(dfp), npoly, static_cast<float*>(dout));
     if (rc) return rc;
     if (st) {
         rc = mr_copy_back(ctx, xy_out, dout, bytes);

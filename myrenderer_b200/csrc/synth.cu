@@ -47,8 +47,41 @@ __device__ __forceinline__ void sincos_turn(double t, double* s_out, double* c_o
     }
 }
 
+// one vertex of a synthetic polygon (families: include/myrenderer_b200.h); same operations, same order as
+// oracle/o_synth.c, every f64 operation separately rounded
+__device__ __forceinline__ float2 synth_vertex(int family, uint64_t key, uint32_t n, uint32_t k) {
+    const double inv24 = 1.0 / 16777216.0;
+    const uint64_t h = mr_mix64(key + k);
+    const double u1 = __dmul_rn((double)(h >> 40), inv24);
+    const double u2 = __dmul_rn((double)((h >> 16) & 0xFFFFFFull), inv24);
+    if (family == MR_FAMILY_ZIPPER) {
+        const uint32_t na = (n + 1u) / 2u;
+        const uint32_t level = k < na ? 2u * k : 2u * (n - 1u - k) + 1u;
+        const double y = __dadd_rn(10.0, __dmul_rn(180.0, __ddiv_rn(__dadd_rn((double)level, __dadd_rn(0.1, __dmul_rn(0.8, u1))), (double)n)));
+        const double x = __dadd_rn(k < na ? 105.0 : 10.0, __dmul_rn(85.0, u2));
+        return make_float2((float)x, (float)y);
+    }
+    double t = __ddiv_rn(__dadd_rn((double)k, __dsub_rn(__dmul_rn(0.8, u1), 0.4)), (double)n);
+    if (t < 0.0) t = __dadd_rn(t, 1.0);
+    double s, c;
+    sincos_turn(t, &s, &c);
+    if (family == MR_FAMILY_ELLIPSE) {
+        const uint64_t g = mr_mix64(key ^ 0x5bd1e9955bd1e995ull);
+        const double a = __dadd_rn(40.0, __dmul_rn(50.0, __dmul_rn((double)(g >> 40), inv24)));
+        const double b = __dadd_rn(40.0, __dmul_rn(50.0, __dmul_rn((double)((g >> 16) & 0xFFFFFFull), inv24)));
+        const double ph = __dmul_rn((double)(mr_mix64(g) >> 40), inv24);
+        double sp, cp;
+        sincos_turn(ph, &sp, &cp);
+        const double ex = __dmul_rn(a, c), ey = __dmul_rn(b, s);
+        return make_float2((float)__dadd_rn(100.0, __dsub_rn(__dmul_rn(cp, ex), __dmul_rn(sp, ey))),
+                           (float)__dadd_rn(100.0, __dadd_rn(__dmul_rn(sp, ex), __dmul_rn(cp, ey))));
+    }
+    const double radius = __dadd_rn(20.0, __dmul_rn(70.0, u2));
+    return make_float2((float)__dadd_rn(100.0, __dmul_rn(radius, c)), (float)__dadd_rn(100.0, __dmul_rn(radius, s)));
+}
+
 // one warp per polygon, lanes over vertices
-__global__ void synth_polygons_k(uint64_t seed, uint64_t poly_index0, const uint64_t* __restrict__ first_point,
+__global__ void synth_polygons_k(int family, uint64_t seed, uint64_t poly_index0, const uint64_t* __restrict__ first_point,
                                  uint32_t npoly, float* __restrict__ xy_out) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -59,16 +92,9 @@ __global__ void synth_polygons_k(uint64_t seed, uint64_t poly_index0, const uint
         const uint32_t n = (uint32_t)(first_point[i + 1] - first_point[i]);
         const uint64_t key = mr_mix64(seed ^ mr_mix64((poly_index0 + i) ^ 0xA5A5A5A5A5A5A5A5ull));
         for (uint32_t k = lane; k < n; k += 32) {
-            const uint64_t h = mr_mix64(key + k);
-            const double u1 = __dmul_rn((double)(h >> 40), 1.0 / 16777216.0);
-            const double u2 = __dmul_rn((double)((h >> 16) & 0xFFFFFFull), 1.0 / 16777216.0);
-            double t = __ddiv_rn(__dadd_rn((double)k, __dsub_rn(__dmul_rn(0.8, u1), 0.4)), (double)n);
-            const double radius = __dadd_rn(20.0, __dmul_rn(70.0, u2));
-            if (t < 0.0) t = __dadd_rn(t, 1.0);
-            double s, c;
-            sincos_turn(t, &s, &c);
-            xy_out[2 * (p0 + k)] = (float)__dadd_rn(100.0, __dmul_rn(radius, c));
-            xy_out[2 * (p0 + k) + 1] = (float)__dadd_rn(100.0, __dmul_rn(radius, s));
+            const float2 v = synth_vertex(family, key, n, k);
+            xy_out[2 * (p0 + k)] = v.x;
+            xy_out[2 * (p0 + k) + 1] = v.y;
         }
     }
 }
@@ -87,13 +113,13 @@ int mr_synth_heightmap_u16_impl(mr_context* ctx, uint64_t seed, uint32_t n, uint
     return MR_OK;
 }
 
-int mr_synth_polygons_impl(mr_context* ctx, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point_dev,
+int mr_synth_polygons_impl(mr_context* ctx, int family, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point_dev,
                            uint32_t npoly, float* xy_dev) {
     if (npoly == 0) return MR_OK;
     uint64_t blocks = ((uint64_t)npoly + 7) / 8;
     const uint64_t cap = (uint64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    synth_polygons_k<<<(unsigned)blocks, 256, 0, ctx->stream>>>(seed, poly_index0, first_point_dev, npoly, xy_dev);
+    synth_polygons_k<<<(unsigned)blocks, 256, 0, ctx->stream>>>(family, seed, poly_index0, first_point_dev, npoly, xy_dev);
     MR_LAUNCH_CHECK(ctx, "synth_polygons_k");
     return MR_OK;
 }

@@ -79,6 +79,8 @@ void mr_o_tri_destroy(mr_o_tri* t);
 /* Returns a MR_POLY_* status word.  stats may be NULL. */
 uint32_t mr_o_tri_create_polygon(mr_o_tri* t, const float* xy, uint32_t n, mr_o_unirand rng,
                                  void* ctx, mr_o_emit_fn emit, mr_o_stats* stats);
+/* Test-only: multiply the contract caps MR_NODE_CAP / MR_STACK_CAP (1 = contract; safety valve 2^27). */
+void mr_o_test_lift_caps(uint32_t multiplier);
 /* Introspection for tests: node arena after the last create_polygon. */
 uint32_t mr_o_tri_node_count(const mr_o_tri* t);
 const mr_o_node* mr_o_tri_nodes(const mr_o_tri* t);
@@ -106,6 +108,8 @@ void mr_o_synth_polygon_sizes(uint64_t seed, uint64_t poly_index0, uint32_t npol
                               uint32_t nmax, int dist, uint64_t* first_point_out);
 void mr_o_synth_polygons(uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
                          uint32_t npoly, float* xy_out);
+void mr_o_synth_polygons_family(int family, uint64_t seed, uint64_t poly_index0,
+                                const uint64_t* first_point, uint32_t npoly, float* xy_out);
 
 int mr_o_hardware_threads(void);
 

@@ -80,25 +80,58 @@ static void sincos_turn(double t, double* s_out, double* c_out) {
     }
 }
 
-void mr_o_synth_polygons(uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
-                         uint32_t npoly, float* xy_out) {
+/* One vertex of a synthetic polygon (definitions in include/myrenderer_b200.h, MR_FAMILY_*). */
+static void synth_vertex(int family, uint64_t key, uint32_t n, uint32_t k, float* x_out, float* y_out) {
+    uint64_t h = mix64(key + k);
+    double u1 = (double)(h >> 40) * (1.0 / 16777216.0);
+    double u2 = (double)((h >> 16) & 0xFFFFFFu) * (1.0 / 16777216.0);
+    if (family == MR_FAMILY_ZIPPER) {
+        /* two y-monotone chains on strictly interleaved levels: vertices 0..ceil(n/2)-1 walk down the
+         * right chain on the even levels, the rest walk up the left chain on the odd levels */
+        uint32_t na = (n + 1u) / 2u;
+        uint32_t level = k < na ? 2u * k : 2u * (n - 1u - k) + 1u;
+        double y = 10.0 + 180.0 * (((double)level + (0.1 + 0.8 * u1)) / (double)n);
+        double x = k < na ? 105.0 + 85.0 * u2 : 10.0 + 85.0 * u2;
+        *x_out = (float)x;
+        *y_out = (float)y;
+    } else {
+        double t = ((double)k + (0.8 * u1 - 0.4)) / (double)n;
+        double s, c;
+        if (t < 0.0) t = t + 1.0;
+        sincos_turn(t, &s, &c);
+        if (family == MR_FAMILY_ELLIPSE) {
+            /* convex: points of an ellipse (semi-axes 40..90) rotated by a per-polygon phase */
+            uint64_t g = mix64(key ^ 0x5bd1e9955bd1e995ull);
+            double a = 40.0 + 50.0 * ((double)(g >> 40) * (1.0 / 16777216.0));
+            double b = 40.0 + 50.0 * ((double)((g >> 16) & 0xFFFFFFu) * (1.0 / 16777216.0));
+            double ph = (double)(mix64(g) >> 40) * (1.0 / 16777216.0);
+            double sp, cp, ex, ey;
+            sincos_turn(ph, &sp, &cp);
+            ex = a * c;
+            ey = b * s;
+            *x_out = (float)(100.0 + (cp * ex - sp * ey));
+            *y_out = (float)(100.0 + (sp * ex + cp * ey));
+        } else { /* MR_FAMILY_STAR */
+            double radius = 20.0 + 70.0 * u2;
+            *x_out = (float)(100.0 + radius * c);
+            *y_out = (float)(100.0 + radius * s);
+        }
+    }
+}
+
+void mr_o_synth_polygons_family(int family, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
+                                uint32_t npoly, float* xy_out) {
     uint32_t i;
     for (i = 0; i < npoly; ++i) {
         uint64_t p0 = first_point[i] - first_point[0];
         uint32_t n = (uint32_t)(first_point[i + 1] - first_point[i]);
         uint64_t key = mix64(seed ^ mix64((poly_index0 + i) ^ 0xA5A5A5A5A5A5A5A5ull));
         uint32_t k;
-        for (k = 0; k < n; ++k) {
-            uint64_t h = mix64(key + k);
-            double u1 = (double)(h >> 40) * (1.0 / 16777216.0);
-            double u2 = (double)((h >> 16) & 0xFFFFFFu) * (1.0 / 16777216.0);
-            double t = ((double)k + (0.8 * u1 - 0.4)) / (double)n;
-            double radius = 20.0 + 70.0 * u2;
-            double s, c;
-            if (t < 0.0) t = t + 1.0;
-            sincos_turn(t, &s, &c);
-            xy_out[2u * (p0 + k)] = (float)(100.0 + radius * c);
-            xy_out[2u * (p0 + k) + 1u] = (float)(100.0 + radius * s);
-        }
+        for (k = 0; k < n; ++k) synth_vertex(family, key, n, k, &xy_out[2u * (p0 + k)], &xy_out[2u * (p0 + k) + 1u]);
     }
+}
+
+void mr_o_synth_polygons(uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
+                         uint32_t npoly, float* xy_out) {
+    mr_o_synth_polygons_family(MR_FAMILY_STAR, seed, poly_index0, first_point, npoly, xy_out);
 }

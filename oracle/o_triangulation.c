@@ -43,6 +43,19 @@ struct mr_o_tri {
     mr_o_stats* stats;
 };
 
+/* Test-only switch (tests/test_oracle_cpu.py::test_arena_caps_are_not_a_divergence): multiplies the contract
+ * caps (safety valve at 2^27 entries; the reference has no bound at all, but its DFS re-pushes a
+ * merged trapezoid once per DAG path and pass 2 is quadratic in the stack, so an unbounded run of
+ * an exploding polygon does not end in practical time -- measured: 3,203 such polygons, 8 threads,
+ * > 15 minutes and 5 GB without finishing).  The test shows that every polygon the contract caps
+ * abandon is still not finished correctly with caps many times larger. */
+static uint32_t g_caps_mult = 1;
+void mr_o_test_lift_caps(uint32_t multiplier) { g_caps_mult = multiplier ? multiplier : 1u; }
+static uint32_t lifted(uint32_t cap) {
+    const uint64_t v = (uint64_t)cap * g_caps_mult;
+    return v > (1u << 27) ? (1u << 27) : (uint32_t)v;
+}
+
 mr_o_tri* mr_o_tri_new(void) { /* :427-435 */
     return (mr_o_tri*)calloc(1, sizeof(mr_o_tri));
 }
@@ -410,8 +423,8 @@ uint32_t mr_o_tri_create_polygon(mr_o_tri* t, const float* xy, uint32_t n, mr_o_
     t->status = MR_POLY_OK;
     t->stats = stats;
     t->nmount = 0;
-    t->node_cap = MR_NODE_CAP(n);
-    t->stack_cap = MR_STACK_CAP(n);
+    t->node_cap = lifted(MR_NODE_CAP(n));
+    t->stack_cap = lifted(MR_STACK_CAP(n));
 
     t->root_node = add_node(t, T_TRAPEZOID); /* :479 */
 

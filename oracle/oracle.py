@@ -85,6 +85,11 @@ def lib() -> C.CDLL:
         L.mr_o_synth_polygons.restype = None
         L.mr_o_synth_polygons.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
                                           C.c_void_p]
+        L.mr_o_synth_polygons_family.restype = None
+        L.mr_o_synth_polygons_family.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32,
+                                                 C.c_void_p]
+        L.mr_o_test_lift_caps.restype = None
+        L.mr_o_test_lift_caps.argtypes = [C.c_uint32]
         L.mr_o_hardware_threads.restype = C.c_int
         L.mr_o_tri_new.restype = C.c_void_p
         L.mr_o_tri_destroy.argtypes = [C.c_void_p]
@@ -251,12 +256,20 @@ def synth_polygon_sizes(seed, npoly, nmin, nmax, dist=0, poly_index0=0) -> np.nd
     return fp
 
 
-def synth_polygons(seed, first_point, poly_index0=0) -> np.ndarray:
+FAMILY_STAR, FAMILY_ELLIPSE, FAMILY_ZIPPER = 0, 1, 2
+
+
+def synth_polygons(seed, first_point, poly_index0=0, family=FAMILY_STAR) -> np.ndarray:
     first_point = np.ascontiguousarray(first_point, dtype=np.uint64)
     npts = int(first_point[-1] - first_point[0])
     xy = np.empty((npts, 2), dtype=np.float32)
-    lib().mr_o_synth_polygons(seed, poly_index0, _ptr(first_point), len(first_point) - 1, _ptr(xy))
+    lib().mr_o_synth_polygons_family(family, seed, poly_index0, _ptr(first_point), len(first_point) - 1, _ptr(xy))
     return xy
+
+
+def lift_caps(multiplier: int):
+    """Test-only: multiply the contract caps of the oracle (1 restores them)."""
+    lib().mr_o_test_lift_caps(multiplier)
 
 
 def atan2f(y, x) -> float:
