@@ -15,12 +15,23 @@ indices all written), inputs resident in HBM.  The polygon throughput of the sam
 "polygons".  `e2e` is the same terrain metric through the reference-facing C-ABI call with pinned
 HOST buffers (H2D of the heightmap and D2H of vertices + indices inside the timed region).
 
+The same line also carries, at every N (strong scaling: the total work is fixed, cut into N shards):
+    config4   BASELINE configs[3]: 16384^2 terrain, row bands; compute-only and -- N > 1 -- with the
+              vertex bands stored straight into rank 0's buffer over NVLink (rank 0 generates the
+              whole index buffer locally)
+    config5   BASELINE configs[4]: 1,000,000 polygons, sizes log-uniform 8..1024, cost-balanced
+              ranges, for the two families the reference triangulates correctly (convex ellipses and
+              the non-convex zipper family); compute-only and gathered into rank 0's buffer
+and, for N > 1, `gather` (the weak-scaled terrain built into rank 0's buffer, checked against a local
+build), plus `single_polygon_us` (N = 1): Polygon.create_polygon's own call shape.
+
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import statistics
@@ -39,6 +50,11 @@ SEED_TERRAIN = 0x5EED0001
 SEED_POLY = 0x5EED0003
 POLY_NMIN, POLY_NMAX = 8, 64
 STRIDE = 32
+CFG4_N, CFG4_SEED = 16384, 0x5EED0004
+CFG5_NPOLY, CFG5_SEED = 1_000_000, 0x5EED0005
+FAMILY_STAR, FAMILY_ELLIPSE, FAMILY_ZIPPER = 0, 1, 2
+APP_POLYGON1 = [[62.742857, 106.97143], [93.085712, 65.828571], [147.08571, 85.628572], [122.14285, 144.77143],
+                [102.34286, 93.857142], [79.199998, 130.37143], [81.00000, 105.17143]]  # App/App.zig:68-76
 
 
 def terrain_size(world: int) -> int:
@@ -56,6 +72,19 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fresh_traffic():
+    """DRAM bytes per launch of the vertex kernel from an `ncu --set full` capture -- only when the capture was
+    taken from THIS terrain.cu (the file's sha256 is stored beside it); otherwise None."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))["terrain_vertices_k"]
+        src = hashlib.sha256(open(os.path.join(ROOT, "myrenderer_b200", "csrc", "terrain.cu"), "rb").read()).hexdigest()
+        if tj.get("terrain_cu_sha256") == src:
+            return int(tj["traffic"]), tj.get("source")
+    except Exception:
+        pass
+    return None, None
 
 
 class ClockSampler:
@@ -100,6 +129,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_name(world: int) -> str:
+    n = terrain_size(world)
+    return (f"terrain {n}x{n} u16 hash-noise heightmap -> pos+normal vertices (32 B) + u32 indices, "
+            f"row-band sharded x{world}; {POLYS_PER_GPU * world} star polygons n in [{POLY_NMIN},{POLY_NMAX}], "
+            f"cost-balanced x{world}")
+
+
+def config_dict(world: int) -> dict:
+    """The `config` object -- the SAME for the b200 arm and the reference arm."""
+    return {"workload": workload_name(world), "terrain_n": terrain_size(world), "polygons": POLYS_PER_GPU * world,
+            "l2": "256 MiB buffer written between timed iterations; each step also writes >1.2 GB",
+            "timing": "b200 arm: CUDA events on the launching stream, value = vertices / (vertex kernel + index kernel) "
+                      "time, max over ranks; reference arm: wall clock of the CPU port on a bounded sample"}
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_rates(world: int, nthreads: int, budget_polys: int = 200_000):
     """Times the CPU oracle (C restatement of the Zig source, prints removed) on a bounded sample of
@@ -128,6 +172,29 @@ def cpu_reference_rates(world: int, nthreads: int, budget_polys: int = 200_000):
     }
 
 
+def cpu_config5_rates(nthreads: int, sample: int = 4000):
+    """CPU port on the first `sample` polygons of config 5 (both sound families)."""
+    from oracle import oracle as O
+
+    fp = O.synth_polygon_sizes(CFG5_SEED, sample, 8, 1024, dist=1)
+    out = {"sample": f"first {sample} of the 1,000,000 polygons", "points": int(fp[-1])}
+    for name, fam in (("ellipse", FAMILY_ELLIPSE), ("zipper", FAMILY_ZIPPER)):
+        xy = O.synth_polygons(CFG5_SEED, fp, family=fam)
+        t0 = time.perf_counter()
+        O.polygon_batch(xy, fp, seed=CFG5_SEED, nthreads=nthreads, want_ids=False)
+        dt = time.perf_counter() - t0
+        out[name] = {"polygons_per_s": sample / dt, "mpoints_per_s": int(fp[-1]) / dt / 1e6}
+    return out
+
+
+def cpu_single_polygon_us(reps: int = 20000):
+    """The CPU port on App.zig's polygon1, one call per polygon with reusable arenas (timed inside C)."""
+    from oracle import oracle as O
+
+    O.time_create_polygon(APP_POLYGON1, 3, 2, 2000)  # warm-up
+    return O.time_create_polygon(APP_POLYGON1, 3, 2, reps) * 1e6
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Zig reference cannot
     be built here (no Zig toolchain, un-vendored deps), so this is the C restatement (oracle port)
@@ -151,11 +218,14 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (last["terrain_s"] + last["polygons_s"]), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus)},
+        "config": config_dict(args.gpus),
         "polygons": {"value": statistics.mean(tp), "unit": "polygons/s"},
+        "config5": cpu_config5_rates(T),
+        "single_polygon_us": cpu_single_polygon_us(),
         "cpu_baseline": {"value": val, "unit": "Mverts/s", "cores": T, "kind": "port",
                          "sample": last["sample"], "polygons_per_s": statistics.mean(tp),
-                         "note": "CPU = C restatement of the Zig source (oracle/), not the Zig binary"},
+                         "note": "CPU = naive C restatement of the Zig source (oracle/), not the Zig binary; mean of "
+                                 f"{args.steps} runs after {args.warmup} warm-ups"},
         "e2e": {"value": val, "unit": "Mverts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -173,13 +243,6 @@ def emit(line: dict):
         os.write(_STDOUT_FD, data)
 
 
-def workload_name(world: int) -> str:
-    n = terrain_size(world)
-    return (f"terrain {n}x{n} u16 hash-noise heightmap -> pos+normal vertices (32 B) + u32 indices, "
-            f"row-band sharded x{world}; {POLYS_PER_GPU * world} star polygons n in [{POLY_NMIN},{POLY_NMAX}], "
-            f"cost-balanced x{world}")
-
-
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -189,8 +252,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", action="store_true",
-                    help="N>1: also time building the terrain bands straight into rank 0's buffer over NVLink (IPC peer stores)")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NVLink gather legs (they are on by default)")
+    ap.add_argument("--no-configs45", action="store_true", help="skip the BASELINE config 4 / config 5 legs")
+    ap.add_argument("--gather", action="store_true", help="(accepted for compatibility: the gather is on by default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
@@ -225,6 +289,81 @@ def main():
     T = mr.Terrain(ctx)
     P = mr.Polygon(ctx)
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(fn, reps, warm=1):
+        """Device time of fn per call: events around each call, barrier between calls, mean; max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        ts = []
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+            barrier()
+        return reduce_max(sum(ts) / len(ts))
+
+    def shared_buffer(nbytes):
+        """rank 0 allocates; the other ranks map it through CUDA IPC (peer pointer over NVLink)."""
+        base = C.c_void_p()
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            ctx.check(lib.mr_device_alloc(ctx.handle, nbytes, C.byref(base)), "alloc gather buffer")
+            hb = (C.c_ubyte * 64)()
+            ctx.check(lib.mr_ipc_export(ctx.handle, base, hb), "ipc export")
+            handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            hb = (C.c_ubyte * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
+            ctx.check(lib.mr_ipc_open(ctx.handle, hb, C.byref(base)), "ipc open")
+        return base
+
+    def release(base):
+        barrier()
+        if rank != 0:
+            lib.mr_ipc_close(ctx.handle, base)
+        barrier()
+        if rank == 0:
+            lib.mr_device_free(ctx.handle, base)
+
+    def checksum(ptr, nbytes):
+        """64-bit sum of the buffer's u64 words (nbytes multiple of 8), computed on the device in chunks."""
+        total = 0
+        chunk = 1 << 30
+        tmp = torch.empty(min(chunk, nbytes) // 8, dtype=torch.int64, device=dev)
+        off = 0
+        while off < nbytes:
+            m = min(chunk, nbytes - off)
+            ctx.check(lib.mr_copy(ctx.handle, tmp.data_ptr(), ptr + off, m), "copy")
+            ctx.sync()
+            total = (total + int(tmp[: m // 8].sum().item())) & 0xFFFFFFFFFFFFFFFF
+            off += m
+        return total
+
     # ---- this rank's shard ---------------------------------------------------------------------
     n = terrain_size(world)
     rows_p = (C.c_uint32 * (world + 1))()
@@ -258,41 +397,15 @@ def main():
     pntri = torch.empty(npoly, dtype=torch.int32, device=dev)
     job_p = P.job(xy, fp_d, npoly, vtx_out=pvtx, first_tri=ft_d, bbox_out=pbbox, status_out=pstat, ntri_out=pntri,
                   seed=SEED_POLY, poly_index0=pa, point_base=int(fp[0]))
-    # second polygon workload: convex polygons of the same sizes (every one is triangulated correctly by the
-    # reference algorithm, so all of them end with status OK)
-    from myrenderer_b200.workloads import ellipse_batch
-
-    cxy, _ = ellipse_batch(fp, 0xC0 + pa, device=dev)
+    # second polygon workload: convex polygons of the same sizes (MR_FAMILY_ELLIPSE: every one is triangulated
+    # correctly by the reference algorithm, so all of them end with status OK)
+    cxy = torch.empty(npts * 2, dtype=torch.float32, device=dev)
+    ctx.check(lib.mr_synth_polygons_family(ctx.handle, FAMILY_ELLIPSE, SEED_POLY, pa, fp_d.data_ptr(), npoly, cxy.data_ptr()), "synth")
     cstat = torch.empty(npoly, dtype=torch.int32, device=dev)
     job_c = P.job(cxy, fp_d, npoly, vtx_out=pvtx, first_tri=ft_d, bbox_out=pbbox, status_out=cstat, ntri_out=pntri,
                   seed=SEED_POLY, poly_index0=pa, point_base=int(fp[0]))
-    # third polygon workload: a bounded sample of BASELINE config 5 (sizes log-uniform 8..1024, convex) per GPU
-    LARGE_PER_GPU = 50_000
-    fpl_all = np.zeros(LARGE_PER_GPU * world + 1, dtype=np.uint64)
-    lib.mr_synth_polygon_sizes(0x5EED0005, 0, LARGE_PER_GPU * world, 8, 1024, 1, fpl_all.ctypes.data)
-    lranges = (C.c_uint32 * (world + 1))()
-    lib.mr_polygon_partition(fpl_all.ctypes.data, LARGE_PER_GPU * world, world, lranges)
-    la, lb = lranges[rank], lranges[rank + 1]
-    fpl = np.ascontiguousarray(fpl_all[la:lb + 1])
-    ftl = mr.polygon_offsets_host(fpl)
-    nl, nl_pts = lb - la, int(fpl[-1] - fpl[0])
-    lxy, _ = ellipse_batch(fpl - fpl[0], 0xC5 + la, device=dev)
-    fpl_d = torch.from_numpy(fpl.view(np.int64)).to(dev)
-    ftl_d = torch.from_numpy(ftl.view(np.int64)).to(dev)
-    lvtx = torch.empty(int(ftl[-1]) * 3 * STRIDE, dtype=torch.uint8, device=dev)
-    lstat = torch.empty(nl, dtype=torch.int32, device=dev)
-    job_l = P.job(lxy, fpl_d, nl, vtx_out=lvtx, first_tri=ftl_d, status_out=lstat, seed=0x5EED0005, poly_index0=la,
-                  point_base=int(fpl[0]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 2x L2
     ctx.sync()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(timers=None):
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
@@ -325,6 +438,9 @@ def main():
     ti = [b.elapsed_time(c) for _, b, c, _ in timers]
     tp = [c.elapsed_time(d) for _, _, c, d in timers]
     ms_v, ms_i, ms_p = (sum(x) / len(x) for x in (tv, ti, tp))
+    ok_star = int((pstat == 0).sum().item())
+    tiers = (C.c_uint32 * 8)()
+    lib.mr_triangulate_tier_counts(ctx.handle, tiers)  # how the star batch was spread over the arena tiers
 
     # ---- convex batch, same protocol -----------------------------------------------------------------
     for _ in range(2):
@@ -341,24 +457,6 @@ def main():
     barrier()
     ms_c = sum(x.elapsed_time(y) for x, y in tc) / len(tc)
     ok_c = int((cstat == 0).sum().item())
-    # ---- large-polygon sample, same protocol -----------------------------------------------------------
-    P.triangulate(job_l)
-    barrier()
-    tl = []
-    for _ in range(max(3, min(args.steps, 5))):
-        a_, b_ = ev(), ev()
-        a_.record()
-        P.triangulate(job_l)
-        b_.record()
-        flush.zero_()
-        tl.append((a_, b_))
-    barrier()
-    ms_l = sum(x.elapsed_time(y) for x, y in tl) / len(tl)
-    ok_l = int((lstat == 0).sum().item())
-    P.triangulate(job_p)  # leave the star batch's statuses in pstat for the report below
-    ctx.sync()
-    tiers = (C.c_uint32 * 8)()
-    lib.mr_triangulate_tier_counts(ctx.handle, tiers)  # how the star batch was spread over the arena tiers
 
     # ---- end to end through the C ABI with pinned host buffers --------------------------------
     e2e = None
@@ -395,115 +493,130 @@ def main():
             te.append(a.elapsed_time(b))
             tpe.append(b.elapsed_time(c))
         barrier()
+        # PCIe floor of the terrain call: the same bytes moved by plain pinned copies (D2H of vertices + indices, H2D of
+        # the heightmap on a second stream -- the two directions overlap), all ranks at once like the call itself
+        side = torch.cuda.Stream()
+        tf = []
+        for _ in range(3):
+            a, b = ev(), ev()
+            barrier()
+            a.record()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                height.copy_(h_height, non_blocking=True)
+            h_vtx.copy_(vtx, non_blocking=True)
+            h_idx.copy_(idx, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(side)
+            b.record()
+            torch.cuda.synchronize()
+            tf.append(a.elapsed_time(b))
+        barrier()
         e2e = {"ms_terrain": sum(te) / len(te), "ms_polygons": sum(tpe) / len(tpe),
                "h2d_terrain": h_height.numel() * 2, "d2h_terrain": h_vtx.numel() + h_idx.numel() * 4,
                "h2d_poly": h_xy.numel() * 4 + fp.nbytes + ft.nbytes,
                "d2h_poly": h_pvtx.numel() + h_bbox.numel() * 4 + h_stat.numel() * 4 + h_ntri.numel() * 4,
-               "status_ok": int((h_stat.numpy() == 0).sum())}
+               "status_ok": int((h_stat.numpy() == 0).sum()), "pcie_floor_ms": min(tf)}
+        del h_vtx, h_idx, h_pvtx, h_height, h_xy
 
-    # ---- N>1: gather into rank 0's buffer by NVLink peer stores (reported separately) -----------------
+    # ---- single polygon: Polygon.create_polygon's own call shape (host pointers, one 7-gon) ------------
+    single = None
+    if world == 1:
+        p1 = np.array(APP_POLYGON1, dtype=np.float32)
+        sfp, sft = np.array([0, 7], dtype=np.uint64), np.array([0, 5], dtype=np.uint64)
+        svtx = np.zeros(5 * 96, dtype=np.uint8)
+        sbb, sst, snt = np.zeros(4, dtype=np.float32), np.zeros(1, dtype=np.uint32), np.zeros(1, dtype=np.uint32)
+        sop = np.array([3, 2], dtype=np.uint32)
+        sj = P.job(p1, sfp, 1, vtx_out=svtx, first_tri=sft, bbox_out=sbb, status_out=sst, ntri_out=snt, offset_prime=sop)
+        for _ in range(50):
+            P.triangulate(sj)
+        l0 = ctx.launch_count
+        ts_ = []
+        for _ in range(1000):
+            t0 = time.perf_counter()
+            P.triangulate(sj)
+            ts_.append(time.perf_counter() - t0)
+        single = {"us": statistics.median(ts_) * 1e6, "p90_us": sorted(ts_)[900] * 1e6,
+                  "launches_per_call": (ctx.launch_count - l0) / 1000, "status": int(sst[0]), "triangles": int(snt[0]),
+                  "what": "mr_triangulate_batch, npoly = 1 (App.zig polygon1), every buffer in host memory, wall clock of "
+                          "the blocking call, median of 1000"}
+
+    # ---- N>1: weak-scaled terrain gathered into rank 0's buffer by NVLink peer stores -------------------
     gather = None
-    if world > 1 and args.gather:
+    want_gather = world > 1 and not args.no_gather
+    if want_gather:
         try:
             total_bytes = n * n * STRIDE
-            handle = torch.zeros(64, dtype=torch.uint8, device=dev)
-            base = C.c_void_p()
-            if rank == 0:
-                ctx.check(lib.mr_device_alloc(ctx.handle, total_bytes, C.byref(base)), "alloc gather buffer")
-                hb = (C.c_ubyte * 64)()
-                ctx.check(lib.mr_ipc_export(ctx.handle, base, hb), "ipc export")
-                handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
-            dist.broadcast(handle, src=0)
-            if rank != 0:
-                hb = (C.c_ubyte * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
-                ctx.check(lib.mr_ipc_open(ctx.handle, hb, C.byref(base)), "ipc open")
+            base = shared_buffer(total_bytes)
             job_g = T.job(height, n, rows=(r0, r1), qrows=(q0, q0), height_row0=lo, height_rows=hi - lo,
                           vtx_out=base.value, vtx_row0=0)  # global row origin: the band lands at its final offset
-            for _ in range(2):
-                T.build(job_g)
+            ms_g = timed(lambda: T.build(job_g), reps=max(3, min(args.steps, 10)), warm=2)
+            # check: every band in rank 0's buffer equals the band its owner built locally (sum of u64 words)
+            T.build(job_v)
+            ctx.sync()
+            local_sum = checksum(vtx.data_ptr(), vtx.numel())
+            sums = torch.tensor([local_sum & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
+            allsums = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(allsums, sums)
             barrier()
-            tg = []
-            for _ in range(max(3, min(args.steps, 10))):
-                a, b = ev(), ev()
-                a.record()
-                T.build(job_g)  # rank g > 0: every vertex store crosses NVLink into rank 0's HBM
-                b.record()
-                torch.cuda.synchronize()
-                tg.append(a.elapsed_time(b))
-                barrier()
-            ms_g = sum(tg) / len(tg)
             ok_gather = True
-            if rank == 0:  # spot-check: the last band (written by the last rank over NVLink) is non-zero
-                chk = torch.empty(1024, dtype=torch.uint8, device=dev)
-                ctx.check(lib.mr_copy(ctx.handle, chk.data_ptr(), base.value + total_bytes - 1024, 1024), "copy")
-                ctx.sync()
-                ok_gather = bool(chk.any().item())
-            gather = {"ms": ms_g, "ok": ok_gather}
-            barrier()
-            if rank != 0:
-                lib.mr_ipc_close(ctx.handle, base)
-            barrier()
             if rank == 0:
-                lib.mr_device_free(ctx.handle, base)
+                for g in range(world):
+                    a_, z_ = rows_p[g] * n * STRIDE, rows_p[g + 1] * n * STRIDE
+                    got = checksum(base.value + a_, z_ - a_) & 0x7FFFFFFFFFFFFFFF
+                    ok_gather = ok_gather and got == int(allsums[g].item())
+            # ceiling for the ingest rate: the same bands moved by plain peer copies (copy engines), all ranks at once
+            def peer_copy():
+                if rank != 0:
+                    ctx.check(lib.mr_copy(ctx.handle, base.value + r0 * n * STRIDE, vtx.data_ptr(), vtx.numel()), "peer copy")
+            ms_pc = timed(peer_copy, reps=3, warm=1)
+            gather = {"ms": ms_g, "ok": bool(ok_gather), "peer_copy_ms": ms_pc}
+            release(base)
         except Exception as exc:  # the gather figure is informative; never lose the main line over it
             gather = {"error": str(exc)[:200]}
 
+    # ---- free the weak-scaling buffers before the full-size configs ---------------------------------------
+    verts_local = (r1 - r0) * n
+    bv, bi = terrain_bytes(n, r1 - r0, q1 - q0)
+    del vtx, idx, height, pvtx, xy, cxy, job_v, job_i, job_p, job_c
+    torch.cuda.empty_cache()
+    lib.mr_context_trim(ctx.handle)
+
+    cfg4 = cfg5 = None
+    if not args.no_configs45:
+        cfg4 = run_config4(ctx, T, dev, rank, world, timed, shared_buffer, release, want_gather, checksum, barrier)
+        torch.cuda.empty_cache()
+        cfg5 = run_config5(ctx, P, dev, rank, world, timed, shared_buffer, release, want_gather, reduce_sum)
+        torch.cuda.empty_cache()
+
     # ---- reduce over ranks: max time, sum of units ------------------------------------------------
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     g_ms_v, g_ms_i, g_ms_p = reduce_max(ms_v), reduce_max(ms_i), reduce_max(ms_p)
     g_ms_terrain = reduce_max(ms_v + ms_i)
     g_ms_step = reduce_max(ms_v + ms_i + ms_p)
-    verts_total = reduce_sum((r1 - r0) * n)
+    verts_total = reduce_sum(verts_local)
     polys_total = reduce_sum(npoly)
-    bv, bi = terrain_bytes(n, r1 - r0, q1 - q0)
     bytes_terrain_total = reduce_sum(bv + bi)
     launches_total = int(reduce_sum(launches))
     if e2e is not None:
         e_ms_t = reduce_max(e2e["ms_terrain"])
         e_ms_p = reduce_max(e2e["ms_polygons"])
+        e_floor = reduce_max(e2e["pcie_floor_ms"])
         e_h2d = int(reduce_sum(e2e["h2d_terrain"] + e2e["h2d_poly"]))
         e_d2h = int(reduce_sum(e2e["d2h_terrain"] + e2e["d2h_poly"]))
-    ok_total = reduce_sum(int((pstat == 0).sum().item()))
+    ok_total = reduce_sum(ok_star)
     g_ms_c = reduce_max(ms_c)
     ok_c_total = reduce_sum(ok_c)
-    g_ms_l = reduce_max(ms_l)
-    ok_l_total, nl_total, nl_pts_total = reduce_sum(ok_l), reduce_sum(nl), reduce_sum(nl_pts)
-    if gather is not None and "ms" in gather:
-        gather["ms"] = reduce_max(gather["ms"])
 
     if rank == 0:
         peak, peak_src = peaks()
         value = verts_total / (g_ms_terrain * 1e-3) / 1e6
         achieved_v = bv / (ms_v * 1e-3) / 1e9  # rank 0's dominant kernel
-        traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["terrain_vertices_k"]
-            if world == 1 and n == 4096:
-                traffic = tj["traffic"]
-        except Exception:
-            traffic = None
+        traffic, traffic_src = fresh_traffic() if (world == 1 and n == 4096) else (None, None)
         line = {
             "metric": "terrain_mverts_per_s",
             "value": value, "unit": "Mverts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": g_ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(world), "terrain_n": n, "polygons": int(polys_total),
-                       "l2": "256 MiB buffer written between timed iterations; each step also writes >1.2 GB",
-                       "timing": "CUDA events on the launching stream; value = vertices / (vertex kernel + index kernel) "
-                                 "time, max over ranks; ms_per_step = terrain + polygon kernels"},
+            "config": config_dict(world),
             "terrain": {"ms": g_ms_terrain, "ms_vertices_kernel": g_ms_v, "ms_indices_kernel": g_ms_i,
                         "achieved_gb_per_s": bytes_terrain_total / (g_ms_terrain * 1e-3) / 1e9,
                         "algorithmic_bytes": int(bytes_terrain_total)},
@@ -513,50 +626,183 @@ def main():
                                  "(overflow/underfill/null-unwrap) on the non-OK fraction and the kernel reproduces that"},
             "polygons_convex": {"value": polys_total / (g_ms_c * 1e-3), "unit": "polygons/s", "ms": g_ms_c,
                                 "status_ok_fraction": ok_c_total / polys_total,
-                                "note": "same sizes, convex (rotated ellipses): the family the reference triangulates correctly"},
-            "polygons_large": {"value": nl_total / (g_ms_l * 1e-3), "unit": "polygons/s", "ms": g_ms_l,
-                               "mpoints_per_s": nl_pts_total / (g_ms_l * 1e-3) / 1e6, "polygons": int(nl_total),
-                               "status_ok_fraction": ok_l_total / nl_total,
-                               "note": "sample of BASELINE config 5: sizes log-uniform 8..1024 (mean 209 points), convex; "
-                                       "the full 1M-polygon run is scripts/bench_configs45.py"},
+                                "note": "same sizes, MR_FAMILY_ELLIPSE (convex): a family the reference triangulates correctly"},
             "polygon_tiers": {"retried_with_contract_cap_arenas": int(sum(tiers[0:6])), "general_path": int(tiers[6]),
                               "note": "rank 0's star batch; everything else ran in the first shared-memory pass"},
             "gpu_launches": launches_total,
             "wall_s_timed_region": wall,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "terrain_vertices_k", "achieved": achieved_v, "peak": peak,
-                         "unit": "GB/s", "frac": achieved_v / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(bv),
+                         "unit": "GB/s", "frac": achieved_v / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(bv),
                          "indices_kernel": {"achieved": bi / (ms_i * 1e-3) / 1e9, "frac": bi / (ms_i * 1e-3) / 1e9 / peak,
                                             "algorithmic_bytes_per_launch": int(bi)}},
         }
+        if cfg4 is not None:
+            line["config4"] = cfg4
+        if cfg5 is not None:
+            line["config5"] = cfg5
         if e2e is not None:
             line["e2e"] = {"value": verts_total / (e_ms_t * 1e-3) / 1e6, "unit": "Mverts/s",
                            "h2d_bytes_per_step": e_h2d, "d2h_bytes_per_step": e_d2h, "ms_terrain": e_ms_t,
                            "ms_polygons": e_ms_p, "polygons_per_s": polys_total / (e_ms_p * 1e-3),
-                           "path": "mr_terrain_build / mr_triangulate_batch with pinned host buffers"}
+                           "pcie_floor_ms": e_floor, "fraction_of_pcie_floor": e_floor / e_ms_t,
+                           "path": "mr_terrain_build / mr_triangulate_batch with pinned host buffers; pcie_floor_ms = the "
+                                   "terrain call's bytes moved by plain pinned copies (both directions at once)"}
+        if single is not None:
+            line["single_polygon_us"] = single["us"]
+            line["single_polygon"] = single
         if gather is not None:
             if "ms" in gather:
                 nv_bytes = n * n * STRIDE * (world - 1) / world
-                gather.update({"what": "terrain vertex bands stored directly into rank 0's buffer (IPC-mapped peer pointer)",
-                               "nvlink_bytes": int(nv_bytes), "rank0_ingest_gb_per_s": nv_bytes / (gather["ms"] * 1e-3) / 1e9})
+                gather.update({"what": "weak-scaled terrain: vertex bands stored directly into rank 0's buffer (IPC-mapped "
+                                       "peer pointer); checked band by band against the local builds",
+                               "nvlink_bytes": int(nv_bytes), "rank0_ingest_gb_per_s": nv_bytes / (gather["ms"] * 1e-3) / 1e9,
+                               "peer_copy_gb_per_s": nv_bytes / (gather["peer_copy_ms"] * 1e-3) / 1e9,
+                               "gather_inclusive_mverts_per_s": verts_total / (gather["ms"] * 1e-3) / 1e6})
             line["gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O  # CPU baseline leg only
 
             Tn = O.hardware_threads()
-            cpu = cpu_reference_rates(1, Tn)
+            cpu_reference_rates(1, Tn, budget_polys=20_000)  # warm-up
+            runs = [cpu_reference_rates(1, Tn) for _ in range(3)]
             cpu1 = cpu_reference_rates(1, 1, budget_polys=20_000)
             line["cpu_baseline"] = {
-                "value": cpu["terrain_mverts_per_s"], "unit": "Mverts/s", "cores": Tn, "kind": "port",
-                "sample": cpu["sample"], "polygons_per_s": cpu["polygons_per_s"],
+                "value": statistics.mean(r["terrain_mverts_per_s"] for r in runs), "unit": "Mverts/s", "cores": Tn,
+                "kind": "port", "sample": runs[-1]["sample"] + "; mean of 3 runs after a warm-up",
+                "polygons_per_s": statistics.mean(r["polygons_per_s"] for r in runs),
                 "single_thread": {"terrain_mverts_per_s": cpu1["terrain_mverts_per_s"],
                                   "polygons_per_s": cpu1["polygons_per_s"], "sample": cpu1["sample"]},
-                "note": "CPU = C restatement of the Zig source (oracle/), prints removed; not the Zig binary"}
+                "config5": cpu_config5_rates(Tn, sample=2000),
+                "single_polygon_us": cpu_single_polygon_us(),
+                "note": "CPU = NAIVE C restatement of the Zig source (oracle/), prints removed; not the Zig binary and "
+                        "not tuned (five divisions per vertex, O(T*M) mountain search as in the reference)"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+def run_config4(ctx, T, dev, rank, world, timed, shared_buffer, release, want_gather, checksum, barrier):
+    """BASELINE configs[3]: 16384^2 terrain, strong-scaled row bands."""
+    import torch
+
+    from myrenderer_b200 import sharding
+
+    lib = ctx.lib
+    n = CFG4_N
+    sh = sharding.plan_terrain(n, rank, world)
+    (r0, r1), (q0, q1), (lo, hi) = sh.rows, sh.qrows, sh.halo_rows
+    height = torch.empty((hi - lo) * n, dtype=torch.int16, device=dev)
+    ctx.check(lib.mr_synth_heightmap_u16(ctx.handle, CFG4_SEED, n, lo, hi - lo, height.data_ptr()), "synth")
+    vtx = torch.empty((r1 - r0) * n * STRIDE, dtype=torch.uint8, device=dev)
+    idx = torch.empty((q1 - q0) * 6 * (n - 1), dtype=torch.int32, device=dev)
+    job_v = T.job(height, n, rows=(r0, r1), qrows=(q0, q0), height_row0=lo, height_rows=hi - lo, vtx_out=vtx, vtx_row0=r0)
+    job_l = T.job(height, n, rows=(r0, r1), qrows=(q0, q1), height_row0=lo, height_rows=hi - lo, vtx_out=vtx, vtx_row0=r0,
+                  idx_out=idx, idx_qrow0=q0)
+    ms_c = timed(lambda: T.build(job_l), reps=5, warm=2)
+    ms_v = timed(lambda: T.build(job_v), reps=5, warm=1)
+    bytes4 = 34 * n * n + 24 * (n - 1) ** 2
+    peak, _ = peaks()
+    res = {"what": "16384 x 16384 heightmap, strong-scaled row bands with a one-row halo",
+           "compute_ms": ms_c, "compute_gverts_per_s": n * n / (ms_c * 1e-3) / 1e9,
+           "achieved_gb_per_s_aggregate": bytes4 / (ms_c * 1e-3) / 1e9,
+           "frac_of_hbm_peak_per_gpu": bytes4 / (ms_c * 1e-3) / 1e9 / world / peak,
+           "vertices_kernel_ms": ms_v, "vertices_kernel_frac_of_hbm_peak": 34 * n * (r1 - r0) / (ms_v * 1e-3) / 1e9 / peak,
+           "algorithmic_bytes": bytes4}
+    if world > 1 and want_gather:
+        try:
+            # one mesh on rank 0: the vertex bands travel over NVLink (peer stores from the kernel), the index buffer --
+            # heightmap-independent, closed form -- is generated by rank 0 locally while the bands arrive
+            local_sum = checksum(vtx.data_ptr(), vtx.numel()) & 0x7FFFFFFFFFFFFFFF
+            del idx
+            torch.cuda.empty_cache()
+            gv = shared_buffer(n * n * STRIDE)
+            gidx = torch.empty(6 * (n - 1) ** 2, dtype=torch.int32, device=dev) if rank == 0 else None
+            if rank == 0:
+                job_g = T.job(height, n, rows=(r0, r1), qrows=(0, n - 1), height_row0=lo, height_rows=hi - lo,
+                              vtx_out=gv.value, vtx_row0=0, idx_out=gidx, idx_qrow0=0)
+            else:
+                job_g = T.job(height, n, rows=(r0, r1), qrows=(0, 0), height_row0=lo, height_rows=hi - lo,
+                              vtx_out=gv.value, vtx_row0=0)
+            ms_g = timed(lambda: T.build(job_g), reps=3, warm=1)
+            import torch.distributed as dist
+
+            sums = torch.tensor([local_sum], dtype=torch.int64, device=dev)
+            allsums = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(allsums, sums)
+            ok = True
+            if rank == 0:
+                rows_p = (C.c_uint32 * (world + 1))()
+                lib.mr_terrain_partition(n, world, rows_p, None)
+                for g in range(world):
+                    a_, z_ = rows_p[g] * n * STRIDE, rows_p[g + 1] * n * STRIDE
+                    ok = ok and (checksum(gv.value + a_, z_ - a_) & 0x7FFFFFFFFFFFFFFF) == int(allsums[g].item())
+            nv = n * n * STRIDE * (world - 1) / world
+            res.update({"gather_ms": ms_g, "gather_gverts_per_s": n * n / (ms_g * 1e-3) / 1e9,
+                        "nvlink_bytes_into_rank0": int(nv), "rank0_ingest_gb_per_s": nv / (ms_g * 1e-3) / 1e9,
+                        "gather_ok": bool(ok),
+                        "gather_note": "vertex bands peer-stored into rank 0; all 6.4 GB of indices generated on rank 0"})
+            del gidx
+            release(gv)
+        except Exception as exc:
+            res["gather_error"] = str(exc)[:200]
+    return res
+
+
+def run_config5(ctx, P, dev, rank, world, timed, shared_buffer, release, want_gather, reduce_sum):
+    """BASELINE configs[4]: 1M polygons, sizes log-uniform 8..1024, strong-scaled cost-balanced ranges."""
+    import torch
+
+    import myrenderer_b200 as mr
+    from myrenderer_b200 import sharding
+
+    lib = ctx.lib
+    npoly = CFG5_NPOLY
+    fp_all = np.zeros(npoly + 1, dtype=np.uint64)
+    lib.mr_synth_polygon_sizes(CFG5_SEED, 0, npoly, 8, 1024, 1, fp_all.ctypes.data)
+    ft_all = mr.polygon_offsets_host(fp_all)
+    ps = sharding.plan_polygons(fp_all, ft_all, rank, world)
+    fp = np.ascontiguousarray(fp_all[ps.begin:ps.end + 1])
+    ft_glob = np.ascontiguousarray(ft_all[ps.begin:ps.end + 1])
+    ft_loc = ft_glob - ft_glob[0]
+    cnt = ps.end - ps.begin
+    fp_d = torch.from_numpy(fp.view(np.int64)).to(dev)
+    ftl_d = torch.from_numpy(ft_loc.view(np.int64)).to(dev)
+    ftg_d = torch.from_numpy(ft_glob.view(np.int64)).to(dev)
+    xy = torch.empty(int(fp[-1] - fp[0]) * 2, dtype=torch.float32, device=dev)
+    pv = torch.empty(int(ft_loc[-1]) * 96, dtype=torch.uint8, device=dev)
+    st = torch.empty(cnt, dtype=torch.int32, device=dev)
+    points = int(fp_all[-1])
+    res = {"what": "1,000,000 polygons, sizes log-uniform 8..1024, strong-scaled cost-balanced contiguous ranges",
+           "points": points, "algorithmic_bytes": int(8 * points + 8 * npoly + 96 * int(ft_all[-1]))}
+    gp = None
+    for name, fam in (("ellipse", FAMILY_ELLIPSE), ("zipper", FAMILY_ZIPPER)):
+        ctx.check(lib.mr_synth_polygons_family(ctx.handle, fam, CFG5_SEED, ps.begin, fp_d.data_ptr(), cnt, xy.data_ptr()), "synth")
+        job = P.job(xy, fp_d, cnt, vtx_out=pv, first_tri=ftl_d, status_out=st, seed=CFG5_SEED, poly_index0=ps.begin,
+                    point_base=int(fp[0]))
+        ms = timed(lambda: P.triangulate(job), reps=2, warm=1)
+        ok = int(reduce_sum(int((st == 0).sum().item())))
+        r = {"compute_ms": ms, "polygons_per_s": npoly / (ms * 1e-3), "mpoints_per_s": points / (ms * 1e-3) / 1e6,
+             "achieved_gb_per_s_aggregate": res["algorithmic_bytes"] / (ms * 1e-3) / 1e9, "status_ok": ok}
+        if world > 1 and want_gather:
+            try:
+                if gp is None:
+                    gp = shared_buffer(int(ft_all[-1]) * 96)
+                jg = P.job(xy, fp_d, cnt, vtx_out=gp.value, first_tri=ftg_d, tri_base=0, status_out=st, seed=CFG5_SEED,
+                           poly_index0=ps.begin, point_base=int(fp[0]))
+                msg = timed(lambda: P.triangulate(jg), reps=2, warm=1)
+                r.update({"gather_ms": msg, "gather_polygons_per_s": npoly / (msg * 1e-3),
+                          "nvlink_bytes_into_rank0": int(int(ft_all[-1]) * 96 * (world - 1) / world)})
+            except Exception as exc:
+                r["gather_error"] = str(exc)[:200]
+        res[name] = r
+    if gp is not None:
+        release(gp)
+    res["note"] = ("ellipse = convex; zipper = non-convex y-monotone family on which the reference is sound for every edge order "
+                   "(tests/test_reference_soundness_cpu.py); every polygon of both ends with status OK")
+    return res
 
 
 if __name__ == "__main__":

@@ -24,8 +24,9 @@
  *     Host pointers are staged through context-owned device scratch (the copy
  *     is part of the call); device pointers are used in place.
  *   - all work is ordered on the context's stream and is asynchronous for
- *     device pointers until mr_sync(); calls that had to stage host memory
- *     return after their results are in the caller's buffer.
+ *     device pointers until mr_sync().  A call that was given ANY host pointer
+ *     (pageable or pinned, input or output) returns only after its inputs have
+ *     been read and its results are in the caller's buffers.
  *   - there is no CPU fallback: without a CUDA device every compute entry
  *     point fails with MR_E_CUDA.
  */
@@ -123,6 +124,11 @@ int mr_sync(mr_context* ctx);
 const char* mr_last_error(const mr_context* ctx);
 /* Kernels launched by this context since creation (monotonic). */
 uint64_t mr_launch_count(const mr_context* ctx);
+/* Host-pointer calls stage through context-owned device scratch that grows to the largest call made
+ * (one 16384^2 host-buffer terrain build holds ~15 GB).  mr_context_trim synchronises and frees all of
+ * it; the next call re-allocates what it needs.  mr_context_scratch_bytes reports the current total. */
+int mr_context_trim(mr_context* ctx);
+int mr_context_scratch_bytes(const mr_context* ctx, uint64_t* bytes_out);
 
 /* ---- plain device-memory helpers for hosts without a CUDA binding (Zig) --- */
 int mr_device_alloc(mr_context* ctx, size_t bytes, void** dev_out);
@@ -151,6 +157,12 @@ int mr_fill_zero(mr_context* ctx, void* dev, size_t bytes);
  *   indices [NEW SPEC]: u32, 6 per quad, quads (r,c) r,c in [0,n-1) row-major, corner order of
  *       Terrain.zig:28-35 under cw front faces (Pipeline.zig:145-149):
  *       (r+1,c) (r,c) (r+1,c+1) (r+1,c+1) (r,c) (r,c+1)   with i(r,c)=r*n+c
+ * Performance note: the quotients by grid_step and 2*grid_step use an exact reciprocal-and-correct
+ * scheme that is enabled only for divisors it has been verified for over all 2^32 dividends
+ * (mr_selftest_fastdiv): grid_step = 0.2f (the reference's constant, divisors 0.2f and 0.4f).  Any
+ * other grid_step is computed with IEEE division -- same results by definition, but the vertex kernel
+ * becomes issue-bound (about 0.6 instead of 0.9 of the HBM roofline).
+ * vtx_out must be 4-byte aligned and idx_out 8-byte aligned (MR_E_BADARG otherwise).
  * The job describes a row band so that one call can be one rank's shard:
  *   vertex (r,c) is written at vtx_out + ((r - vtx_row0)*n + c)*stride for r in [row_begin,row_end)
  *   quad row q is written at idx_out + (q - idx_qrow0)*6*(n-1) for q in [qrow_begin,qrow_end)
@@ -228,9 +240,10 @@ typedef struct mr_polygon_job {
 
 int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job);
 /* Introspection: how the last mr_triangulate_batch on this context spread its polygons over the
- * arena tiers.  out[0..5] = polygons re-run with contract-cap arenas, per size tier (<=64,128,...,1024,
- * >1024); out[6] = polygons handed to the general path (coincident points, not-acute corner, ...);
- * out[7] = polygons of the >1024 tier.  Synchronises the stream. */
+ * arena tiers.  out[0..4] = polygons re-run with contract-cap arenas, by size (<=64, <=128, <=256,
+ * <=512, <=1024 points); out[5] = 0 (reserved); out[6] = polygons handed to the general path
+ * (coincident points, not-acute corner, ...); out[7] = polygons of 1025..MR_MAX_POLYGON_POINTS
+ * points (always general path).  Synchronises the stream. */
 int mr_triangulate_tier_counts(mr_context* ctx, uint32_t out[8]);
 /* first_tri[0..npoly] from first_point[0..npoly] (device or host pointers). */
 int mr_polygon_offsets(mr_context* ctx, const uint64_t* first_point, uint32_t npoly,

@@ -18,18 +18,8 @@ int mr_synth_polygons_impl(mr_context* ctx, int family, uint64_t seed, uint64_t 
                            uint32_t npoly, float* xy_dev);
 
 namespace {
-// unirand.zig:24 (host copy for mr_unirand_seed_host)
-const uint32_t k_primes_host[MR_NPRIMES] = {
-    2,    3,    5,    7,    11,   13,   17,   19,   23,   29,   31,   37,   41,   43,
-    47,   53,   59,   61,   67,   71,   73,   79,   83,   89,   97,   101,  103,  107,
-    109,  113,  127,  131,  137,  139,  149,  151,  157,  163,  167,  173,  179,  181,
-    191,  193,  197,  199,  211,  223,  227,  229,  233,  239,  241,  251,  257,  263,
-    269,  271,  277,  281,  283,  293,  307,  311,  313,  317,  331,  337,  347,  349,
-    353,  359,  367,  373,  379,  383,  389,  397,  401,  409,  419,  421,  431,  433,
-    439,  443,  449,  457,  461,  463,  467,  479,  487,  491,  499,  503,  509,  521,
-    523,  541,  601,  659,  733,  809,  863,  941,  1013, 1069, 1151, 1283, 1289, 1367,
-    1447, 1499, 1579, 1637, 1723, 429494501u, 429493501u, 429486647u, 100001053u, 100002421u,
-    10001567u};
+// unirand.zig:24: host view of the table defined once in unirand.cuh (mr_unirand_seed_host)
+const uint32_t k_primes_host[MR_NPRIMES] = {MR_PRIME_LIST};
 
 bool layout_ok(const mr_layout* L, uint32_t need_attrs, uint32_t ncomp0) {
     if (!L || L->nattr < need_attrs || L->nattr > MR_MAX_ATTR) return false;
@@ -97,6 +87,9 @@ int mr_context_destroy(mr_context* ctx) {
     for (int i = 0; i < MR_NUM_SCRATCH; ++i)
         if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->pinned_mailbox) cudaFreeHost(ctx->pinned_mailbox);
+    if (ctx->small_pinned) cudaFreeHost(ctx->small_pinned);
+    if (ctx->small_dev) cudaFree(ctx->small_dev);
+    mr_polygon_plan_free(ctx);
     for (int i = 0; i < MR_NUM_AUX; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
@@ -104,6 +97,27 @@ int mr_context_destroy(mr_context* ctx) {
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return MR_OK;
+}
+
+int mr_context_trim(mr_context* ctx) {
+    if (!ctx) return MR_E_BADARG;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < MR_NUM_SCRATCH; ++i) {
+        if (ctx->scratch[i]) MR_CUDA(ctx, cudaFree(ctx->scratch[i]));
+        ctx->scratch[i] = nullptr;
+        ctx->scratch_bytes[i] = 0;
+    }
+    ctx->last_header_dev = nullptr;
+    return MR_OK;
+}
+
+int mr_context_scratch_bytes(const mr_context* ctx, uint64_t* bytes_out) {
+    if (!ctx || !bytes_out) return MR_E_BADARG;
+    uint64_t t = 0;
+    for (int i = 0; i < MR_NUM_SCRATCH; ++i) t += ctx->scratch_bytes[i];
+    *bytes_out = t;
     return MR_OK;
 }
 
@@ -226,57 +240,88 @@ int mr_terrain_build(mr_context* ctx, const mr_terrain_job* job) {
     if (j.height_fmt != MR_HEIGHT_U16 && j.height_fmt != MR_HEIGHT_F32) return mr_fail(ctx, MR_E_BADARG, "terrain: bad height_fmt");
     if (j.row_begin > j.row_end || j.row_end > j.n) return mr_fail(ctx, MR_E_BADARG, "terrain: bad row range");
     if (j.qrow_begin > j.qrow_end || j.qrow_end > j.n - 1u) return mr_fail(ctx, MR_E_BADARG, "terrain: bad quad-row range");
+    const bool want_v = j.vtx_out && j.row_end > j.row_begin;
+    const bool want_i = j.idx_out && j.n > 1 && j.qrow_end > j.qrow_begin;
     if (j.vtx_out && !layout_ok(&j.layout, 1, 3)) return mr_fail(ctx, MR_E_BADARG, "terrain: bad vertex layout");
     if (j.vtx_out && j.layout.nattr > 1 && j.layout.attr[1].ncomp < 3) return mr_fail(ctx, MR_E_BADARG, "terrain: normal needs 3 components");
-    if (j.vtx_out && j.row_end > j.row_begin) {
+    if (j.vtx_out && j.vtx_row0 > j.row_begin) return mr_fail(ctx, MR_E_BADARG, "terrain: vtx_row0 > row_begin");
+    if (j.idx_out && j.idx_qrow0 > j.qrow_begin) return mr_fail(ctx, MR_E_BADARG, "terrain: idx_qrow0 > qrow_begin");
+    if (j.vtx_out && (reinterpret_cast<uintptr_t>(j.vtx_out) & 3u)) return mr_fail(ctx, MR_E_BADARG, "terrain: vtx_out must be 4-byte aligned");
+    if (j.idx_out && (reinterpret_cast<uintptr_t>(j.idx_out) & 7u)) return mr_fail(ctx, MR_E_BADARG, "terrain: idx_out must be 8-byte aligned");
+    if (want_v) {
         const uint32_t need_lo = j.row_begin > 0 ? j.row_begin - 1 : 0;
         const uint32_t need_hi = std::min(j.row_end + 1, j.n);
         if (j.height_row0 > need_lo || (uint64_t)j.height_row0 + j.height_rows < need_hi)
             return mr_fail(ctx, MR_E_BADARG, "terrain: height rows do not cover the band plus halo");
-        if (j.vtx_row0 > j.row_begin) return mr_fail(ctx, MR_E_BADARG, "terrain: vtx_row0 > row_begin");
     }
-    if (j.idx_out && j.qrow_end > j.qrow_begin && j.idx_qrow0 > j.qrow_begin) return mr_fail(ctx, MR_E_BADARG, "terrain: idx_qrow0 > qrow_begin");
+    if (!want_v && !want_i) return MR_OK;  // empty band: nothing to produce
     MR_CUDA(ctx, cudaSetDevice(ctx->device));
 
     mr_terrain_job d = j;
-    const size_t texel = j.height_fmt == MR_HEIGHT_U16 ? 2 : 4;
-    const void* hdev = nullptr;
-    int rc = mr_stage_in(ctx, 0, j.height, (size_t)j.height_rows * j.n * texel, &hdev);
-    if (rc) return rc;
-    d.height = hdev;
+    if (!want_v) d.vtx_out = nullptr;
+    if (!want_i) d.idx_out = nullptr;
     bool vs = false, is = false;
     void* vdev = nullptr;
     void* idev = nullptr;
-    const size_t vbytes = (size_t)(j.row_end - j.vtx_row0) * j.n * j.layout.stride;
-    const size_t ibytes = j.n > 1 ? (size_t)(j.qrow_end - j.idx_qrow0) * 6u * (j.n - 1u) * 4u : 0;
-    if (j.vtx_out) {
-        rc = mr_stage_out(ctx, 4, j.vtx_out, vbytes, &vdev, &vs);
+    const size_t row_bytes = (size_t)j.n * j.layout.stride;
+    const size_t qrow_bytes = 6u * (size_t)(j.n - 1u) * 4u;
+    int rc;
+    // The index buffer does not depend on the heightmap.  When it has to travel to a host buffer, it is built and copied
+    // on a side stream first, so that its device-to-host copy overlaps the heightmap's host-to-device copy (PCIe is full
+    // duplex) and the vertex kernel, instead of both copies queueing behind both kernels.
+    cudaStream_t idx_stream = ctx->stream;
+    if (want_i) {
+        // staged output holds quad rows [qrow_begin, qrow_end) only (device outputs keep the caller's idx_qrow0 origin)
+        rc = mr_stage_out(ctx, 5, j.idx_out, (size_t)(j.qrow_end - j.qrow_begin) * qrow_bytes, &idev, &is);
         if (rc) return rc;
-        d.vtx_out = vdev;
+        if (is) {
+            d.idx_out = static_cast<uint32_t*>(idev);
+            d.idx_qrow0 = j.qrow_begin;
+            if (want_v && !mr_is_device_ptr(j.vtx_out)) {
+                if (mr_aux_streams(ctx)) return mr_fail(ctx, MR_E_CUDA, "side streams");
+                MR_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));  // order after earlier work on the context
+                MR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->fork_ev, 0));
+                idx_stream = ctx->aux[0];
+            }
+        }
     }
-    if (j.idx_out) {
-        rc = mr_stage_out(ctx, 5, j.idx_out, ibytes, &idev, &is);
+    if (idx_stream != ctx->stream) {
+        mr_terrain_job di = d;
+        di.vtx_out = nullptr;
+        rc = mr_terrain_build_impl(ctx, &di, idx_stream);
         if (rc) return rc;
-        d.idx_out = static_cast<uint32_t*>(idev);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(j.idx_out) + (size_t)(j.qrow_begin - j.idx_qrow0) * qrow_bytes;
+        MR_CUDA(ctx, cudaMemcpyAsync(dst, idev, (size_t)(j.qrow_end - j.qrow_begin) * qrow_bytes, cudaMemcpyDeviceToHost, idx_stream));
+        MR_CUDA(ctx, cudaEventRecord(ctx->join_ev[0], idx_stream));
+        d.idx_out = nullptr;
     }
-    rc = mr_terrain_build_impl(ctx, &d);
+    if (want_v) {
+        const size_t texel = j.height_fmt == MR_HEIGHT_U16 ? 2 : 4;
+        const void* hdev = nullptr;
+        rc = mr_stage_in(ctx, 0, j.height, (size_t)j.height_rows * j.n * texel, &hdev);
+        if (rc) return rc;
+        d.height = hdev;
+        rc = mr_stage_out(ctx, 4, j.vtx_out, (size_t)(j.row_end - j.row_begin) * row_bytes, &vdev, &vs);
+        if (rc) return rc;
+        if (vs) {
+            d.vtx_out = vdev;
+            d.vtx_row0 = j.row_begin;
+        }
+    }
+    rc = mr_terrain_build_impl(ctx, &d, ctx->stream);
     if (rc) return rc;
     if (vs) {
-        // only rows [row_begin,row_end) were produced
-        const size_t off = (size_t)(j.row_begin - j.vtx_row0) * j.n * j.layout.stride;
-        rc = mr_copy_back(ctx, static_cast<unsigned char*>(j.vtx_out) + off, static_cast<unsigned char*>(vdev) + off,
-                          (size_t)(j.row_end - j.row_begin) * j.n * j.layout.stride);
+        rc = mr_copy_back(ctx, static_cast<unsigned char*>(j.vtx_out) + (size_t)(j.row_begin - j.vtx_row0) * row_bytes, vdev,
+                          (size_t)(j.row_end - j.row_begin) * row_bytes);
         if (rc) return rc;
     }
-    if (is) {
-        const size_t L = 6u * (size_t)(j.n - 1u) * 4u;
-        const size_t off = (size_t)(j.qrow_begin - j.idx_qrow0) * L;
-        rc = mr_copy_back(ctx, reinterpret_cast<unsigned char*>(j.idx_out) + off, static_cast<unsigned char*>(idev) + off,
-                          (size_t)(j.qrow_end - j.qrow_begin) * L);
+    if (is && idx_stream == ctx->stream) {
+        rc = mr_copy_back(ctx, reinterpret_cast<unsigned char*>(j.idx_out) + (size_t)(j.qrow_begin - j.idx_qrow0) * qrow_bytes, idev,
+                          (size_t)(j.qrow_end - j.qrow_begin) * qrow_bytes);
         if (rc) return rc;
     }
-    if (vs || is) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MR_OK;
+    if (idx_stream != ctx->stream) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev[0], 0));
+    return mr_finish_host_io(ctx);
 }
 
 int mr_terrain_build_full(mr_context* ctx, const void* height, uint32_t height_fmt, uint32_t n, const mr_layout* layout,
@@ -313,6 +358,7 @@ int mr_selftest_fastdiv(mr_context* ctx, float divisor, int force_fast, uint64_t
     if (rc) return rc;
     MR_CUDA(ctx, cudaMemcpyAsync(mismatches_out, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->host_io = false;
     return MR_OK;
 }
 
@@ -331,9 +377,8 @@ int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, 
     if (st) {
         rc = mr_copy_back(ctx, out, dout, (size_t)count * 4);
         if (rc) return rc;
-        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    return MR_OK;
+    return mr_finish_host_io(ctx);
 }
 
 int mr_polygon_offsets(mr_context* ctx, const uint64_t* first_point, uint32_t npoly, uint64_t* first_tri_out) {
@@ -351,9 +396,8 @@ int mr_polygon_offsets(mr_context* ctx, const uint64_t* first_point, uint32_t np
     if (st) {
         rc = mr_copy_back(ctx, first_tri_out, dft, (size_t)(npoly + 1) * 8);
         if (rc) return rc;
-        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    return MR_OK;
+    return mr_finish_host_io(ctx);
 }
 
 int mr_polygon_draw_range(uint64_t first_tri_i, uint64_t first_tri_next, uint64_t tri_base, mr_draw_range* out) {
@@ -374,7 +418,12 @@ int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job) {
     if (!j.xy || !j.first_point || !j.first_tri || !j.vtx_out) return mr_fail(ctx, MR_E_BADARG, "polygons: null pointer");
     if (!layout_ok(&j.layout, 1, 2)) return mr_fail(ctx, MR_E_BADARG, "polygons: bad vertex layout");
     if (j.layout.nattr > 1 && j.layout.attr[1].ncomp < 3) return mr_fail(ctx, MR_E_BADARG, "polygons: colour needs 3 components");
+    if (reinterpret_cast<uintptr_t>(j.vtx_out) & 3u) return mr_fail(ctx, MR_E_BADARG, "polygons: vtx_out must be 4-byte aligned");
     MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    {   // the reference's own call shape (Polygon.create_polygon: one small polygon, everything in host memory)
+        int rc_small = MR_OK;
+        if (mr_triangulate_small(ctx, &j, &rc_small)) return rc_small;
+    }
 
     mr_polygon_job d = j;
     const bool fp_dev = mr_is_device_ptr(j.first_point);
@@ -427,6 +476,7 @@ int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job) {
     // 12.3 ms for the 100k batch); pageable host memory is staged and copied back.
     if (void* alias = mr_pinned_device_alias(j.vtx_out)) {
         q = alias;
+        ctx->host_io = true;  // the kernels store into the caller's host buffer: the call returns after they finish
     } else {
         rc = mr_stage_out(ctx, 4, j.vtx_out, vbytes, &q, &sv);
         if (rc) return rc;
@@ -447,7 +497,7 @@ int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job) {
         if (rc) return rc;
         d.ntri_out = static_cast<uint32_t*>(q);
     }
-    rc = mr_triangulate_impl(ctx, &d);
+    rc = mr_triangulate_impl(ctx, &d, fp_dev ? nullptr : j.first_point);
     if (rc) return rc;
     if (sv) {
         // the polygons of this job own [first_tri[0], first_tri[npoly]) only
@@ -463,8 +513,7 @@ int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job) {
     if (sb) { rc = mr_copy_back(ctx, j.bbox_out, d.bbox_out, (size_t)j.npoly * 16); if (rc) return rc; }
     if (ss) { rc = mr_copy_back(ctx, j.status_out, d.status_out, (size_t)j.npoly * 4); if (rc) return rc; }
     if (sn) { rc = mr_copy_back(ctx, j.ntri_out, d.ntri_out, (size_t)j.npoly * 4); if (rc) return rc; }
-    if (sv || sb || ss || sn) MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MR_OK;
+    return mr_finish_host_io(ctx);
 }
 
 int mr_triangulate_tier_counts(mr_context* ctx, uint32_t out[8]) {
@@ -520,9 +569,8 @@ int mr_unirand_seed_batch(mr_context* ctx, const uint64_t* first_point, uint32_t
     if (st) {
         rc = mr_copy_back(ctx, offset_prime_out, dout, (size_t)npoly * 8);
         if (rc) return rc;
-        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    return MR_OK;
+    return mr_finish_host_io(ctx);
 }
 
 int mr_synth_heightmap_u16(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t row0, uint32_t rows, uint16_t* out) {
@@ -538,9 +586,8 @@ int mr_synth_heightmap_u16(mr_context* ctx, uint64_t seed, uint32_t n, uint32_t 
     if (st) {
         rc = mr_copy_back(ctx, out, dout, bytes);
         if (rc) return rc;
-        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    return MR_OK;
+    return mr_finish_host_io(ctx);
 }
 
 int mr_synth_polygons(mr_context* ctx, uint64_t seed, uint64_t poly_index0, const uint64_t* first_point,
@@ -571,9 +618,8 @@ int mr_synth_polygons_family(mr_context* ctx, int family, uint64_t seed, uint64_
     if (st) {
         rc = mr_copy_back(ctx, xy_out, dout, bytes);
         if (rc) return rc;
-        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    return MR_OK;
+    return mr_finish_host_io(ctx);
 }
 
 int mr_ipc_export(mr_context* ctx, void* dev, unsigned char handle_out[MR_IPC_HANDLE_BYTES]) {

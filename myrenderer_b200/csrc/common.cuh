@@ -32,6 +32,17 @@ struct mr_context {
     cudaStream_t aux[MR_NUM_AUX] = {nullptr};
     cudaEvent_t fork_ev = nullptr;
     cudaEvent_t join_ev[MR_NUM_AUX] = {nullptr};
+    // set whenever a call consumed or produced caller HOST memory (staged copy, pinned source, zero-copy alias):
+    // such a call synchronises before it returns (mr_finish_host_io)
+    bool host_io = false;
+    // polygon launch plan (kernel, block, blocks per SM, shared memory per size class), built once per context
+    void* poly_plan = nullptr;
+    // small-batch path: one pinned block + its device mirror (inputs, work list, outputs of a call in one copy each way)
+    void* small_pinned = nullptr;
+    void* small_dev = nullptr;
+    size_t small_bytes = 0;
+    // work-list header of the last mr_triangulate_batch (mr_triangulate_tier_counts)
+    const uint32_t* last_header_dev = nullptr;
 };
 
 inline int mr_aux_streams(mr_context* ctx) {
@@ -116,6 +127,7 @@ inline int mr_stage_in(mr_context* ctx, int slot, const void* src, size_t bytes,
         *dev = src;
         return MR_OK;
     }
+    ctx->host_io = true;  // a pinned source is copied asynchronously: the call must not return before it is read
     void* d = nullptr;
     int rc = mr_scratch(ctx, slot, bytes, &d);
     if (rc) return rc;
@@ -131,11 +143,22 @@ inline int mr_stage_out(mr_context* ctx, int slot, void* dst, size_t bytes, void
         *dev = dst;
         return MR_OK;
     }
+    ctx->host_io = true;
     void* d = nullptr;
     int rc = mr_scratch(ctx, slot, bytes, &d);
     if (rc) return rc;
     *dev = d;
     *staged = true;
+    return MR_OK;
+}
+
+// End of an entry point: if the call touched caller host memory in any way, wait for the stream, so that inputs may
+// be reused and outputs read as soon as the call returns (the header's contract for host pointers).
+inline int mr_finish_host_io(mr_context* ctx) {
+    if (!ctx->host_io) return MR_OK;
+    ctx->host_io = false;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return mr_fail(ctx, MR_E_CUDA, "cudaStreamSynchronize", e);
     return MR_OK;
 }
 
@@ -153,5 +176,10 @@ __host__ __device__ __forceinline__ uint64_t mr_mix64(uint64_t z) {
 }
 
 // internal entry points implemented in the other translation units
-int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* job);
-int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* job);
+// vertices on ctx->stream; the index kernel on idx_stream
+int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* job, cudaStream_t idx_stream);
+// first_point_host: the caller's host copy of first_point when it has one (lets the scheduler skip empty size classes)
+int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* job, const uint64_t* first_point_host);
+// all-host-pointer jobs small enough for the one-block path; returns 1 when it handled the job, 0 when it does not apply
+int mr_triangulate_small(mr_context* ctx, const mr_polygon_job* job, int* rc_out);
+void mr_polygon_plan_free(mr_context* ctx);

@@ -288,7 +288,7 @@ DivConst make_div_const(float b) {
 
 }  // namespace
 
-int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* j) {
+int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* j, cudaStream_t idx_stream) {
     const uint32_t n = j->n;
     if (j->vtx_out && j->row_end > j->row_begin) {
         TerrainArgs a;
@@ -335,7 +335,7 @@ int mr_terrain_build_impl(mr_context* ctx, const mr_terrain_job* j) {
         a.div_magic = ((1ull << 48) / (n - 1u)) + 1ull;
         const uint64_t blocks = (a.quad_count + TI_QUADS - 1) / TI_QUADS;
         if (blocks > 0x7FFFFFFFull) return mr_fail(ctx, MR_E_BADARG, "terrain index range too large for one launch");
-        terrain_indices_k<<<(unsigned)blocks, TI_THREADS, 0, ctx->stream>>>(a);
+        terrain_indices_k<<<(unsigned)blocks, TI_THREADS, 0, idx_stream>>>(a);
         MR_LAUNCH_CHECK(ctx, "terrain_indices_k");
     }
     return MR_OK;

@@ -1143,7 +1143,7 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
 
 // General path (float compares, 12-byte nodes, literal fallback loop), global-memory workspace:
 // which == 0: polygons handed over by the fast path (coincident points, not-acute corner, oversized
-// mountain lists; n <= 1024); which == 1: class 7 (1024 < n <= MR_MAX_POLYGON_POINTS).
+// mountain lists; n <= 1024); which == 1: the last class (1024 < n <= MR_MAX_POLYGON_POINTS).
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_general_k(const BatchArgs a, uint32_t nmax, int which) {
     const Caps caps = tier1_caps(nmax);
     const WsLayout L = ws_layout(caps, false);
@@ -1336,11 +1336,11 @@ int mr_unirand_seed_batch_impl(mr_context* ctx, const uint64_t* first_point_dev,
 
 int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]) {
     memset(out, 0, 8 * sizeof(uint32_t));
-    if (!ctx->scratch[SLOT_WORK]) return MR_OK;
+    if (!ctx->last_header_dev) return MR_OK;
     uint32_t hdr[HEADER_WORDS];
-    MR_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->scratch[SLOT_WORK], sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream));
+    MR_CUDA(ctx, cudaMemcpyAsync(hdr, ctx->last_header_dev, sizeof(hdr), cudaMemcpyDeviceToHost, ctx->stream));
     MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // spec_count per internal class, folded into the documented size tiers <=64, 128, 256, 512, 1024
+    // spec_count per internal class, folded into the documented size tiers <=64, <=128, <=256, <=512, <=1024
     for (int c = 0; c < NUM_CLASSES - 1; ++c) {
         const uint32_t nmax = class_nmax(c);
         const int tier = nmax <= 64u ? 0 : nmax <= 128u ? 1 : nmax <= 256u ? 2 : nmax <= 512u ? 3 : 4;
@@ -1351,42 +1351,114 @@ int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]) {
     return MR_OK;
 }
 
-int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
-    // all pointers in *j are device pointers here (staging happened in api.cu)
-    const uint32_t npoly = j->npoly;
-    if (npoly == 0) return MR_OK;
+// ---- launch plan --------------------------------------------------------------------------------------------
+// Kernel, block shape, blocks per SM and shared memory of every (size class, tier).  The function attributes and
+// occupancy queries behind it cost ~50 driver calls; they are made once per context, not once per batch.
+namespace {
+struct ClassLaunch {
+    const void* kern;  // triangulate_team_k<W> (args: BatchArgs, int) when team > 1, else triangulate_fast_k<..> (BatchArgs, int, int)
+    int team;          // warps cooperating on one polygon (1 = independent warps)
+    int wpb;           // warps per block
+    int per_sm;        // resident blocks per SM
+    size_t smem;       // dynamic shared memory per block
+};
+struct PolyPlan {
+    ClassLaunch first[NUM_CLASSES - 1], spec[NUM_CLASSES - 1];
+};
 
-    // work-list memory: header | hist[NBINS] | cursor[NBINS] | order[npoly] | spec_list[npoly] | general_list[npoly]
-    const size_t header_words = HEADER_WORDS;
-    void* work = nullptr;
-    int rc = mr_scratch(ctx, SLOT_WORK, (header_words + 2 * (size_t)NBINS + 3 * (size_t)npoly) * 4, &work);
-    if (rc) return rc;
-    uint32_t* w = static_cast<uint32_t*>(work);
-    uint32_t* class_begin = w + HDR_CLASS_BEGIN;      // NUM_CLASSES
-    uint32_t* class_end = w + HDR_CLASS_END;          // NUM_CLASSES
-    uint32_t* queue_head = w + HDR_QUEUE_HEAD;        // 2*NUM_CLASSES + 2
-    uint32_t* spec_count = w + HDR_SPEC_COUNT;        // NUM_CLASSES
-    uint32_t* general_count = w + HDR_GENERAL_COUNT;  // 1
-    uint32_t* hist = w + header_words;
-    uint32_t* cursor = hist + NBINS;
-    uint32_t* order = cursor + NBINS;
-    uint32_t* spec_list = order + npoly;
-    uint32_t* general_list = spec_list + npoly;
-    MR_CUDA(ctx, cudaMemsetAsync(w, 0, (header_words + 2 * (size_t)NBINS) * 4, ctx->stream));
+int build_plan(mr_context* ctx, PolyPlan* plan) {
+    for (int spec = 0; spec < 2; ++spec) {
+        for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+            ClassLaunch& out = spec ? plan->spec[c] : plan->first[c];
+            const FCaps caps = fast_caps(c, spec != 0);
+            const FLayout L = fast_layout(caps);
+            if (!fast_layout_ok(caps, L)) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace layout is inconsistent");
+            if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
+            const int team = spec ? 1 : team_warps(c);
+            if (team > 1) {  // one polygon per block, `team` warps per polygon
+                void (*kern)(const BatchArgs, int) = nullptr;  // one instantiation per team width: see team_warps
+                switch (team) {
+                    case 3: kern = triangulate_team_k<3>; break;
+                    case 4: kern = triangulate_team_k<4>; break;
+                    case 6: kern = triangulate_team_k<6>; break;
+                    case 8: kern = triangulate_team_k<8>; break;
+                }
+                if (!kern) return mr_fail(ctx, MR_E_CUDA, "no team kernel of this width");
+                MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+                int per_sm = 0;
+                MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, L.total));
+                out = {reinterpret_cast<const void*>(kern), team, team, per_sm < 1 ? 1 : per_sm, L.total};
+            } else {
+                // independent warps, 4, 2 or 1 per block: whichever puts the most polygons on an SM (ties: larger blocks)
+                void (*kern)(const BatchArgs, int, int) = triangulate_fast_k<false, -1>;  // retry tiers
+                if (!spec) {
+                    switch (c) {
+                        case 0: kern = triangulate_fast_k<false, 0>; break;
+                        // (compile-time class constants were measured for the other kernels too: no gain for the
+                        // single-warp conflict-list classes, 8 % slower for the team kernels)
+                        case 1: case 2: case 3: case 4: case 5: kern = triangulate_fast_k<true, -1>; break;
+                        default: return mr_fail(ctx, MR_E_CUDA, "no single-warp kernel for this class");
+                    }
+                }
+                // one attribute per kernel function: the largest block any class launches it with
+                int wpb = 1, per_sm = 1;
+                for (int w = MAX_WARPS_PER_BLOCK; w >= 1; w >>= 1) {
+                    if (L.total * w > ctx->smem_optin) continue;
+                    cudaFuncAttributes fa;
+                    MR_CUDA(ctx, cudaFuncGetAttributes(&fa, kern));
+                    if ((size_t)fa.maxDynamicSharedSizeBytes < L.total * w)
+                        MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(L.total * w)));
+                    int b = 0;
+                    MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, w * 32, L.total * w));
+                    if (b * w > per_sm * wpb || (w == MAX_WARPS_PER_BLOCK && b >= 1)) {
+                        wpb = w;
+                        per_sm = b;
+                    }
+                }
+                out = {reinterpret_cast<const void*>(kern), 1, wpb, per_sm, L.total * wpb};
+            }
+        }
+    }
+    return MR_OK;
+}
 
-    const unsigned cblocks = (unsigned)std::min<uint64_t>(((uint64_t)npoly + 255) / 256, (uint64_t)ctx->sm_count * 2);
-    size_hist_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, hist);
-    MR_LAUNCH_CHECK(ctx, "size_hist_k");
-    size_scan_k<<<1, 1024, 0, ctx->stream>>>(hist, cursor, class_begin, class_end);
-    MR_LAUNCH_CHECK(ctx, "size_scan_k");
-    size_scatter_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, cursor, order);
-    MR_LAUNCH_CHECK(ctx, "size_scatter_k");
+int get_plan(mr_context* ctx, PolyPlan** plan_out) {
+    if (!ctx->poly_plan) {
+        PolyPlan* p = new (std::nothrow) PolyPlan();
+        if (!p) return mr_fail(ctx, MR_E_NOMEM, "polygon launch plan");
+        const int rc = build_plan(ctx, p);
+        if (rc) {
+            delete p;
+            return rc;
+        }
+        ctx->poly_plan = p;
+    }
+    *plan_out = static_cast<PolyPlan*>(ctx->poly_plan);
+    return MR_OK;
+}
 
-    BatchArgs a;
+// launches class c's kernel of the given tier; `units` = polygons it can possibly find in its queue (bounds the grid)
+int launch_class(mr_context* ctx, const ClassLaunch& L, BatchArgs& a, int c, int spec, cudaStream_t st, uint32_t units) {
+    uint64_t grid = (uint64_t)ctx->sm_count * L.per_sm;
+    const uint64_t need = L.team > 1 ? units : ((uint64_t)units + L.wpb - 1) / L.wpb;
+    if (need < grid) grid = need ? need : 1;
+    if (L.team > 1) {
+        void* args[] = {&a, &c};
+        MR_CUDA(ctx, cudaLaunchKernel(L.kern, dim3((unsigned)grid), dim3(L.wpb * 32), args, L.smem, st));
+    } else {
+        void* args[] = {&a, &c, &spec};
+        MR_CUDA(ctx, cudaLaunchKernel(L.kern, dim3((unsigned)grid), dim3(L.wpb * 32), args, L.smem, st));
+    }
+    MR_LAUNCH_CHECK(ctx, L.team > 1 ? "triangulate_team_k" : "triangulate_fast_k");
+    return MR_OK;
+}
+
+void fill_batch_args(BatchArgs& a, const mr_polygon_job* j, uint32_t* header, uint32_t* order, uint32_t* spec_list,
+                     uint32_t* general_list) {
     a.xy = j->xy;
     a.first_point = j->first_point;
     a.point_base = j->point_base;
-    a.npoly = npoly;
+    a.npoly = j->npoly;
     a.offset_prime = j->offset_prime;
     a.seed = j->seed;
     a.poly_index0 = j->poly_index0;
@@ -1405,105 +1477,310 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j) {
                    ? 1
                    : 0;
     a.order = order;
-    a.class_begin = class_begin;
-    a.class_end = class_end;
-    a.queue_head = queue_head;
+    a.class_begin = header + HDR_CLASS_BEGIN;
+    a.class_end = header + HDR_CLASS_END;
+    a.queue_head = header + HDR_QUEUE_HEAD;
     a.spec_list = spec_list;
-    a.spec_count = spec_count;
+    a.spec_count = header + HDR_SPEC_COUNT;
     a.general_list = general_list;
-    a.general_count = general_count;
+    a.general_count = header + HDR_GENERAL_COUNT;
     a.tier1_ws = nullptr;
     a.tier1_ws_stride = 0;
     a.par_ws = nullptr;
+}
+
+// global scratch of the n <= 64 kernel's parallel search: one slice per warp of its full grid
+int class0_scratch(mr_context* ctx, const PolyPlan& plan, BatchArgs& a) {
+    void* pw = nullptr;
+    const ClassLaunch& L0 = plan.first[0];
+    const int rc = mr_scratch(ctx, SLOT_PAR, (size_t)ctx->sm_count * L0.per_sm * L0.wpb * PAR_GL_BYTES, &pw);
+    if (rc) return rc;
+    a.par_ws = static_cast<unsigned char*>(pw);
+    return MR_OK;
+}
+
+// general path: global-memory workspaces, one per warp of the grid.  which == 0: polygons handed over by the fast
+// path; which == 1: the 1025..MR_MAX_POLYGON_POINTS class.
+int launch_general(mr_context* ctx, BatchArgs& a, int which, uint32_t units) {
+    const uint32_t nmax = which == 0 ? class_nmax(NUM_CLASSES - 2) : MR_MAX_POLYGON_POINTS;
+    const Caps c1 = tier1_caps(nmax);
+    const WsLayout L1 = ws_layout(c1, false);
+    const int wpb = which == 0 ? 4 : 1;
+    uint64_t blocks = (uint64_t)ctx->sm_count;
+    const uint64_t need = ((uint64_t)units + wpb - 1) / wpb;
+    if (need < blocks) blocks = need ? need : 1;
+    void* t1 = nullptr;
+    const int rc = mr_scratch(ctx, which == 0 ? SLOT_TIER1 : SLOT_TIER1B, (size_t)blocks * wpb * L1.total, &t1);
+    if (rc) return rc;
+    a.tier1_ws = static_cast<unsigned char*>(t1);
+    a.tier1_ws_stride = L1.total;
+    triangulate_general_k<<<(unsigned)blocks, wpb * 32, 0, ctx->stream>>>(a, nmax, which);
+    MR_LAUNCH_CHECK(ctx, "triangulate_general_k");
+    return MR_OK;
+}
+}  // namespace
+
+void mr_polygon_plan_free(mr_context* ctx) {
+    delete static_cast<PolyPlan*>(ctx->poly_plan);
+    ctx->poly_plan = nullptr;
+}
+
+int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j, const uint64_t* first_point_host) {
+    // all pointers in *j are device pointers here (staging happened in api.cu)
+    const uint32_t npoly = j->npoly;
+    if (npoly == 0) return MR_OK;
+    PolyPlan* plan = nullptr;
+    int rc = get_plan(ctx, &plan);
+    if (rc) return rc;
+
+    // work-list memory: header | hist[NBINS] | cursor[NBINS] | order[npoly] | spec_list[npoly] | general_list[npoly]
+    const size_t header_words = HEADER_WORDS;
+    void* work = nullptr;
+    rc = mr_scratch(ctx, SLOT_WORK, (header_words + 2 * (size_t)NBINS + 3 * (size_t)npoly) * 4, &work);
+    if (rc) return rc;
+    uint32_t* w = static_cast<uint32_t*>(work);
+    uint32_t* hist = w + header_words;
+    uint32_t* cursor = hist + NBINS;
+    uint32_t* order = cursor + NBINS;
+    uint32_t* spec_list = order + npoly;
+    uint32_t* general_list = spec_list + npoly;
+    ctx->last_header_dev = w;
+    MR_CUDA(ctx, cudaMemsetAsync(w, 0, (header_words + 2 * (size_t)NBINS) * 4, ctx->stream));
+
+    const unsigned cblocks = (unsigned)std::min<uint64_t>(((uint64_t)npoly + 255) / 256, (uint64_t)ctx->sm_count * 2);
+    size_hist_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, hist);
+    MR_LAUNCH_CHECK(ctx, "size_hist_k");
+    size_scan_k<<<1, 1024, 0, ctx->stream>>>(hist, cursor, w + HDR_CLASS_BEGIN, w + HDR_CLASS_END);
+    MR_LAUNCH_CHECK(ctx, "size_scan_k");
+    size_scatter_k<<<cblocks, 256, 0, ctx->stream>>>(j->first_point, npoly, cursor, order);
+    MR_LAUNCH_CHECK(ctx, "size_scatter_k");
+
+    // Polygons per class: known exactly when the caller's first_point lives on the host (then empty classes cost no
+    // launch at all); otherwise every class may hold up to npoly polygons and its kernel finds out on the device.
+    uint32_t count[NUM_CLASSES];
+    for (int c = 0; c < NUM_CLASSES; ++c) count[c] = first_point_host ? 0u : npoly;
+    if (first_point_host)
+        for (uint32_t i = 0; i < npoly; ++i) {
+            const uint64_t n = first_point_host[i + 1] - first_point_host[i];
+            ++count[class_of(n > MR_MAX_POLYGON_POINTS ? 0u : (uint32_t)n)];  // invalid sizes ride in bin 0 (size_bin)
+        }
+
+    BatchArgs a;
+    fill_batch_args(a, j, w, order, spec_list, general_list);
+    if (count[0]) {
+        rc = class0_scratch(ctx, *plan, a);
+        if (rc) return rc;
+    }
 
     // fast path: per class, first with typical-case arenas, then the overflow with contract-cap arenas.  The first pass
     // runs class after class on the caller's stream (measured: running the classes concurrently costs the 1M-polygon
     // batch 4 %, the large classes lose SM residency to the small ones; splitting off only the n <= 64 class gains
-    // nothing).  The second pass is ten mostly empty kernels: each goes to its own side stream, so their launch
+    // nothing).  The second pass is up to ten mostly empty kernels: each goes to its own side stream, so their launch
     // latencies overlap; the caller's stream forks and joins around it.
     static_assert(NUM_CLASSES - 1 <= MR_NUM_AUX, "one side stream per shared-memory class");
-    if (mr_aux_streams(ctx)) return mr_fail(ctx, MR_E_CUDA, "side streams");
-    for (int spec = 0; spec < 2; ++spec) {
-        if (spec) MR_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
-        for (int c = 0; c < NUM_CLASSES - 1; ++c) {
-            cudaStream_t st = spec ? ctx->aux[c] : ctx->stream;
-            if (spec) MR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork_ev, 0));
-            const FCaps caps = fast_caps(c, spec != 0);
-            const FLayout L = fast_layout(caps);
-            if (!fast_layout_ok(caps, L)) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace layout is inconsistent");
-            const int team = spec ? 1 : team_warps(c);
-            if (team > 1) {  // one polygon per block, `team` warps per polygon
-                const size_t smem = L.total;
-                if (smem > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                void (*kern)(const BatchArgs, int) = nullptr;  // one instantiation per team width: see team_warps
-                switch (team) {
-                    case 3: kern = triangulate_team_k<3>; break;
-                    case 4: kern = triangulate_team_k<4>; break;
-                    case 6: kern = triangulate_team_k<6>; break;
-                    case 8: kern = triangulate_team_k<8>; break;
-                }
-                if (!kern) return mr_fail(ctx, MR_E_CUDA, "no team kernel of this width");
-                MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int per_sm = 0;
-                MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, team * 32, smem));
-                if (per_sm < 1) per_sm = 1;
-                kern<<<(unsigned)(ctx->sm_count * per_sm), team * 32, smem, st>>>(a, c);
-                MR_LAUNCH_CHECK(ctx, "triangulate_team_k");
-            } else {
-                // independent warps, 4, 2 or 1 per block: whichever puts the most polygons on an SM (ties: larger blocks)
-                if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
-                void (*kern)(const BatchArgs, int, int) = triangulate_fast_k<false, -1>;  // retry tiers
-                if (!spec) {
-                    switch (c) {
-                        case 0: kern = triangulate_fast_k<false, 0>; break;
-                        // (compile-time class constants were measured for the other kernels too: no gain for the
-                        // single-warp conflict-list classes, 8 % slower for the team kernels)
-                        case 1: case 2: case 3: case 4: case 5: kern = triangulate_fast_k<true, -1>; break;  // (class 5 only when it is not a team class)
-                        default: return mr_fail(ctx, MR_E_CUDA, "no single-warp kernel for this class");
-                    }
-                }
-                MR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)std::min<size_t>(L.total * MAX_WARPS_PER_BLOCK, ctx->smem_optin)));
-                int wpb = 1, per_sm = 1;
-                for (int w = MAX_WARPS_PER_BLOCK; w >= 1; w >>= 1) {
-                    if (L.total * w > ctx->smem_optin) continue;
-                    int b = 0;
-                    MR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, w * 32, L.total * w));
-                    if (b * w > per_sm * wpb || (w == MAX_WARPS_PER_BLOCK && b >= 1)) {
-                        wpb = w;
-                        per_sm = b;
-                    }
-                }
-                const size_t smem = L.total * wpb;
-                if (c == 0 && !spec) {  // global scratch of the parallel search, one slice per warp of the grid
-                    void* pw = nullptr;
-                    rc = mr_scratch(ctx, SLOT_PAR, (size_t)ctx->sm_count * per_sm * wpb * PAR_GL_BYTES, &pw);
-                    if (rc) return rc;
-                    a.par_ws = static_cast<unsigned char*>(pw);
-                }
-                const unsigned grid = (unsigned)(ctx->sm_count * per_sm);
-                kern<<<grid, wpb * 32, smem, st>>>(a, c, spec);
-                MR_LAUNCH_CHECK(ctx, "triangulate_fast_k");
-            }
-            if (spec) MR_CUDA(ctx, cudaEventRecord(ctx->join_ev[c], st));
-        }
-        if (spec)
-            for (int c = 0; c < NUM_CLASSES - 1; ++c) MR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c], 0));
-    }
-    // general path: global-memory workspaces, one per warp of the grid
-    for (int which = 0; which < 2; ++which) {
-        const uint32_t nmax = which == 0 ? class_nmax(NUM_CLASSES - 2) : MR_MAX_POLYGON_POINTS;
-        const Caps c1 = tier1_caps(nmax);
-        const WsLayout L1 = ws_layout(c1, false);
-        const int wpb = which == 0 ? 4 : 1;
-        const unsigned blocks = (unsigned)ctx->sm_count;
-        void* t1 = nullptr;
-        rc = mr_scratch(ctx, which == 0 ? SLOT_TIER1 : SLOT_TIER1B, (size_t)blocks * wpb * L1.total, &t1);
+    for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+        if (!count[c]) continue;
+        rc = launch_class(ctx, plan->first[c], a, c, 0, ctx->stream, count[c]);
         if (rc) return rc;
-        a.tier1_ws = static_cast<unsigned char*>(t1);
-        a.tier1_ws_stride = L1.total;
-        triangulate_general_k<<<blocks, wpb * 32, 0, ctx->stream>>>(a, nmax, which);
-        MR_LAUNCH_CHECK(ctx, "triangulate_general_k");
+    }
+    if (mr_aux_streams(ctx)) return mr_fail(ctx, MR_E_CUDA, "side streams");
+    MR_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+    int first_error = MR_OK;
+    bool forked[NUM_CLASSES - 1] = {false};
+    for (int c = 0; c < NUM_CLASSES - 1 && !first_error; ++c) {
+        if (!count[c]) continue;
+        cudaStream_t st = ctx->aux[c];
+        if (cudaStreamWaitEvent(st, ctx->fork_ev, 0) != cudaSuccess) { first_error = mr_fail(ctx, MR_E_CUDA, "cudaStreamWaitEvent"); break; }
+        forked[c] = true;
+        first_error = launch_class(ctx, plan->spec[c], a, c, 1, st, count[c]);
+    }
+    for (int c = 0; c < NUM_CLASSES - 1; ++c) {  // join every stream that was forked, also on the error path
+        if (!forked[c]) continue;
+        if (cudaEventRecord(ctx->join_ev[c], ctx->aux[c]) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c], 0) != cudaSuccess)
+            if (!first_error) first_error = mr_fail(ctx, MR_E_CUDA, "side-stream join");
+    }
+    if (first_error) return first_error;
+    // general path
+    uint32_t shared_total = 0;
+    for (int c = 0; c < NUM_CLASSES - 1; ++c) shared_total += count[c];
+    if (shared_total) {
+        rc = launch_general(ctx, a, 0, first_point_host ? shared_total : npoly);
+        if (rc) return rc;
+    }
+    if (count[NUM_CLASSES - 1]) {
+        rc = launch_general(ctx, a, 1, count[NUM_CLASSES - 1]);
+        if (rc) return rc;
     }
     return MR_OK;
+}
+
+// ---- small-batch path -----------------------------------------------------------------------------------------
+// The reference's own call (Polygon.create_polygon, Polygon.zig:81-107; App.zig:68-83) triangulates ONE small polygon
+// whose points, vertex buffer and bounding box all live in host memory.  For such jobs the batch machinery above is
+// almost pure overhead (work-list kernels, a dozen staging copies, twenty launches).  Here the whole call is
+//     one host->device copy   [xy | first_point | first_tri | offset_prime | order | header]      (work list built on the host)
+//     one kernel per non-empty size class (one for App.zig's polygons)
+//     one device->host copy   [header | status | ntri | bbox | vertices]
+//     one stream synchronisation
+// through a pinned block owned by the context.  The header comes back with the outputs; only if it reports polygons
+// that outgrew their first-pass arenas (rare) are the retry tiers launched and the outputs copied again.
+namespace {
+constexpr uint32_t SMALL_MAX_POLYS = 2048;
+constexpr size_t SMALL_MAX_BYTES = 8u << 20;
+inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+}  // namespace
+
+int mr_triangulate_small(mr_context* ctx, const mr_polygon_job* jp, int* rc_out) {
+    const mr_polygon_job& j = *jp;
+    *rc_out = MR_OK;
+    const uint32_t npoly = j.npoly;
+    if (npoly == 0 || npoly > SMALL_MAX_POLYS) return 0;
+    // every buffer in plain host memory (a pinned vertex buffer takes the zero-copy route of the batch path)
+    const void* ptrs[] = {j.xy, j.first_point, j.first_tri, j.vtx_out, j.offset_prime, j.bbox_out, j.status_out, j.ntri_out};
+    for (const void* p : ptrs) {
+        if (!p) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            continue;  // unregistered host memory
+        }
+        if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 0;
+        if (p == j.vtx_out && at.type == cudaMemoryTypeHost) return 0;
+    }
+    if (j.first_point[0] < j.point_base || j.first_tri[0] < j.tri_base) return 0;  // the batch path reports it
+    const uint64_t pts0 = j.first_point[0] - j.point_base, npts = j.first_point[npoly] - j.first_point[0];
+    const uint64_t tri0 = j.first_tri[0] - j.tri_base, ntri = j.first_tri[npoly] - j.first_tri[0];
+    const size_t vbytes = (size_t)ntri * 3u * j.layout.stride;
+    // block layout
+    size_t o = 0;
+    const size_t o_xy = o;    o += up16((size_t)npts * 8);
+    const size_t o_fp = o;    o += up16((size_t)(npoly + 1) * 8);
+    const size_t o_ft = o;    o += up16((size_t)(npoly + 1) * 8);
+    const size_t o_op = o;    o += j.offset_prime ? up16((size_t)npoly * 8) : 0;
+    const size_t o_order = o; o += up16((size_t)npoly * 4);
+    const size_t o_hdr = o;   o += up16((size_t)HEADER_WORDS * 4);
+    const size_t in_end = o;
+    const size_t o_stat = o;  o += up16((size_t)npoly * 4);
+    const size_t o_ntri = o;  o += up16((size_t)npoly * 4);
+    const size_t o_bbox = o;  o += up16((size_t)npoly * 16);
+    const size_t o_vtx = (o + 31) & ~(size_t)31;
+    o = o_vtx + up16(vbytes);
+    const size_t out_end = o;
+    const size_t o_spec = o;  o += up16((size_t)npoly * 4);   // device only
+    const size_t o_gen = o;   o += up16((size_t)npoly * 4);   // device only
+    if (npts > (1u << 20) || o > SMALL_MAX_BYTES) return 0;
+
+    auto fail = [&](int rc) { *rc_out = rc; return 1; };
+    PolyPlan* plan = nullptr;
+    int rc = get_plan(ctx, &plan);
+    if (rc) return fail(rc);
+    if (ctx->small_bytes < o) {
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(mr_fail(ctx, MR_E_CUDA, "sync"));
+        if (ctx->small_pinned) cudaFreeHost(ctx->small_pinned);
+        if (ctx->small_dev) cudaFree(ctx->small_dev);
+        ctx->small_pinned = ctx->small_dev = nullptr;
+        ctx->small_bytes = 0;
+        const size_t want = std::max<size_t>(o * 2, 64u << 10);
+        if (cudaMallocHost(&ctx->small_pinned, want) != cudaSuccess || cudaMalloc(&ctx->small_dev, want) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(mr_fail(ctx, MR_E_NOMEM, "small-batch block"));
+        }
+        ctx->small_bytes = want;
+    }
+    unsigned char* hb = static_cast<unsigned char*>(ctx->small_pinned);
+    unsigned char* db = static_cast<unsigned char*>(ctx->small_dev);
+
+    // ---- inputs and the work list, built on the host ------------------------------------------------------
+    memcpy(hb + o_xy, j.xy + 2 * pts0, (size_t)npts * 8);
+    uint64_t* fp = reinterpret_cast<uint64_t*>(hb + o_fp);
+    uint64_t* ft = reinterpret_cast<uint64_t*>(hb + o_ft);
+    for (uint32_t i = 0; i <= npoly; ++i) {  // rebased: the block's xy / vertex arrays start at this job's first entries
+        fp[i] = j.first_point[i] - j.first_point[0];
+        ft[i] = j.first_tri[i] - j.first_tri[0];
+    }
+    if (j.offset_prime) memcpy(hb + o_op, j.offset_prime, (size_t)npoly * 8);
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(hb + o_hdr);
+    uint32_t* order = reinterpret_cast<uint32_t*>(hb + o_order);
+    memset(hdr, 0, (size_t)HEADER_WORDS * 4);
+    uint32_t count[NUM_CLASSES] = {0};
+    auto cls = [&](uint32_t i) {
+        const uint64_t n = fp[i + 1] - fp[i];
+        return class_of(n > MR_MAX_POLYGON_POINTS ? 0u : (uint32_t)n);
+    };
+    for (uint32_t i = 0; i < npoly; ++i) ++count[cls(i)];
+    {   // queue order: class by class; inside a class largest first (stable counting sort on the size, like size_scatter_k
+        // up to the order among equal sizes, which does not affect results)
+        uint32_t begin[NUM_CLASSES], run = 0;
+        for (int c = NUM_CLASSES - 1; c >= 0; --c) {  // descending sizes overall: class 10 first, like the device sort
+            begin[c] = run;
+            hdr[HDR_CLASS_BEGIN + c] = run;
+            run += count[c];
+            hdr[HDR_CLASS_END + c] = run;
+        }
+        std::vector<std::pair<uint32_t, uint32_t>> keyed(npoly);
+        for (uint32_t i = 0; i < npoly; ++i) keyed[i] = {(uint32_t)std::min<uint64_t>(fp[i + 1] - fp[i], 0xFFFFFFFFull), i};
+        std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+        uint32_t cur[NUM_CLASSES];
+        for (int c = 0; c < NUM_CLASSES; ++c) cur[c] = begin[c];
+        for (uint32_t k = 0; k < npoly; ++k) order[cur[cls(keyed[k].second)]++] = keyed[k].second;
+    }
+    MR_CUDA(ctx, cudaMemcpyAsync(db, hb, in_end, cudaMemcpyHostToDevice, ctx->stream));
+
+    mr_polygon_job d = j;
+    d.xy = reinterpret_cast<const float*>(db + o_xy);
+    d.first_point = reinterpret_cast<const uint64_t*>(db + o_fp);
+    d.point_base = 0;
+    d.first_tri = reinterpret_cast<const uint64_t*>(db + o_ft);
+    d.tri_base = 0;
+    d.offset_prime = j.offset_prime ? reinterpret_cast<const uint32_t*>(db + o_op) : nullptr;
+    d.vtx_out = db + o_vtx;
+    d.bbox_out = reinterpret_cast<float*>(db + o_bbox);
+    d.status_out = reinterpret_cast<uint32_t*>(db + o_stat);
+    d.ntri_out = reinterpret_cast<uint32_t*>(db + o_ntri);
+    BatchArgs a;
+    fill_batch_args(a, &d, reinterpret_cast<uint32_t*>(db + o_hdr), reinterpret_cast<uint32_t*>(db + o_order),
+                    reinterpret_cast<uint32_t*>(db + o_spec), reinterpret_cast<uint32_t*>(db + o_gen));
+    ctx->last_header_dev = reinterpret_cast<const uint32_t*>(db + o_hdr);
+    if (count[0]) {
+        rc = class0_scratch(ctx, *plan, a);
+        if (rc) return fail(rc);
+    }
+    for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+        if (!count[c]) continue;
+        rc = launch_class(ctx, plan->first[c], a, c, 0, ctx->stream, count[c]);
+        if (rc) return fail(rc);
+    }
+    if (count[NUM_CLASSES - 1]) {
+        rc = launch_general(ctx, a, 1, count[NUM_CLASSES - 1]);
+        if (rc) return fail(rc);
+    }
+    auto fetch = [&]() -> int {
+        MR_CUDA(ctx, cudaMemcpyAsync(hb + o_hdr, db + o_hdr, out_end - o_hdr, cudaMemcpyDeviceToHost, ctx->stream));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return MR_OK;
+    };
+    rc = fetch();
+    if (rc) return fail(rc);
+    // ---- rare: polygons that outgrew the first-pass arenas ---------------------------------------------------
+    uint32_t respec = 0;
+    for (int c = 0; c < NUM_CLASSES - 1; ++c) respec += hdr[HDR_SPEC_COUNT + c];
+    if (respec || hdr[HDR_GENERAL_COUNT]) {
+        for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+            if (!hdr[HDR_SPEC_COUNT + c]) continue;
+            rc = launch_class(ctx, plan->spec[c], a, c, 1, ctx->stream, hdr[HDR_SPEC_COUNT + c]);
+            if (rc) return fail(rc);
+        }
+        // the spec tier may hand polygons on to the general path: its count is only known on the device
+        rc = launch_general(ctx, a, 0, respec + hdr[HDR_GENERAL_COUNT]);
+        if (rc) return fail(rc);
+        rc = fetch();
+        if (rc) return fail(rc);
+    }
+    // ---- outputs --------------------------------------------------------------------------------------------
+    memcpy(static_cast<unsigned char*>(j.vtx_out) + (size_t)tri0 * 3u * j.layout.stride, hb + o_vtx, vbytes);
+    if (j.status_out) memcpy(j.status_out, hb + o_stat, (size_t)npoly * 4);
+    if (j.ntri_out) memcpy(j.ntri_out, hb + o_ntri, (size_t)npoly * 4);
+    if (j.bbox_out) memcpy(j.bbox_out, hb + o_bbox, (size_t)npoly * 16);
+    ctx->host_io = false;
+    return 1;
 }

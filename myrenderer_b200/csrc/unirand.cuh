@@ -13,18 +13,15 @@
 #define MR_GOLDEN 0x9E3779B97F4A7C15ull
 #define MR_NPRIMES 123
 
-// unirand.zig:24, in the reference's order
-__device__ __constant__ uint32_t k_unirand_primes_dev[MR_NPRIMES] = {
-    2,    3,    5,    7,    11,   13,   17,   19,   23,   29,   31,   37,   41,   43,
-    47,   53,   59,   61,   67,   71,   73,   79,   83,   89,   97,   101,  103,  107,
-    109,  113,  127,  131,  137,  139,  149,  151,  157,  163,  167,  173,  179,  181,
-    191,  193,  197,  199,  211,  223,  227,  229,  233,  239,  241,  251,  257,  263,
-    269,  271,  277,  281,  283,  293,  307,  311,  313,  317,  331,  337,  347,  349,
-    353,  359,  367,  373,  379,  383,  389,  397,  401,  409,  419,  421,  431,  433,
-    439,  443,  449,  457,  461,  463,  467,  479,  487,  491,  499,  503,  509,  521,
-    523,  541,  601,  659,  733,  809,  863,  941,  1013, 1069, 1151, 1283, 1289, 1367,
-    1447, 1499, 1579, 1637, 1723, 429494501u, 429493501u, 429486647u, 100001053u, 100002421u,
-    10001567u};
+// unirand.zig:24, in the reference's order -- the one product copy of the table (device array here, host array in api.cu)
+#define MR_PRIME_LIST                                                                                       \
+    2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 101, 103, 107,  \
+    109, 113, 127, 131, 137, 139, 149, 151, 157, 163, 167, 173, 179, 181, 191, 193, 197, 199, 211, 223, 227, 229,   \
+    233, 239, 241, 251, 257, 263, 269, 271, 277, 281, 283, 293, 307, 311, 313, 317, 331, 337, 347, 349, 353, 359,   \
+    367, 373, 379, 383, 389, 397, 401, 409, 419, 421, 431, 433, 439, 443, 449, 457, 461, 463, 467, 479, 487, 491,   \
+    499, 503, 509, 521, 523, 541, 601, 659, 733, 809, 863, 941, 1013, 1069, 1151, 1283, 1289, 1367, 1447, 1499,     \
+    1579, 1637, 1723, 429494501u, 429493501u, 429486647u, 100001053u, 100002421u, 10001567u
+__device__ __constant__ uint32_t k_unirand_primes_dev[MR_NPRIMES] = {MR_PRIME_LIST};
 
 __host__ __device__ __forceinline__ uint64_t mr_rng_state0_hd(uint64_t seed, uint64_t index) {
     return seed ^ (MR_GOLDEN * (index + 1ull));

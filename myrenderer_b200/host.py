@@ -347,18 +347,28 @@ class Polygon:
                             self.layout)
 
     def create_polygon(self, vertices, *, offset_prime=None, seed=0, index=0) -> PolygonObj:
-        """Polygon.create_polygon(vertices): one polygon -> VertexBuffer of n-2 triangles + bbox."""
+        """Polygon.create_polygon(vertices): one polygon -> VertexBuffer of n-2 triangles + bbox.
+
+        Like the reference (Polygon.zig:82-92: a mapped-at-creation buffer filled by the emit callback) the
+        vertex range is HOST memory -- the stand-in for the mapped range -- so the call takes the library's
+        small-batch path: one copy in, one kernel, one copy out."""
         v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 2)
-        if len(v) < 2:  # Polygon.zig:82: vertices.len - 2 underflows
+        n = len(v)
+        if n < 2:  # Polygon.zig:82: vertices.len - 2 underflows
             raise ValueError("a polygon needs at least 2 vertices")
-        op = None if offset_prime is None else np.asarray(offset_prime, dtype=np.uint32).reshape(1, 2)
-        b = self.create_polygons(v, np.array([0, len(v)], dtype=np.uint64), offset_prime=op, seed=seed,
-                                 poly_index0=index)
-        self.ctx.sync()
-        bb = b.bbox.cpu().numpy()[0]
-        vb = b.draw_range(0)
+        op = None if offset_prime is None else np.ascontiguousarray(offset_prime, dtype=np.uint32).reshape(2)
+        fp = np.array([0, n], dtype=np.uint64)
+        ft = np.array([0, n - 2], dtype=np.uint64)
+        mapped = np.zeros(max((n - 2) * 3 * self.layout.stride, 1), dtype=np.uint8)  # VertexBuffer.new: zeroed
+        bb = np.zeros(4, dtype=np.float32)
+        st = np.zeros(1, dtype=np.uint32)
+        nt = np.zeros(1, dtype=np.uint32)
+        self.triangulate(self.job(v, fp, 1, vtx_out=mapped, first_tri=ft, bbox_out=bb, status_out=st, ntri_out=nt,
+                                  offset_prime=op, seed=seed, poly_index0=index))
+        buf = torch.from_numpy(mapped) if torch is not None else mapped
+        vb = VertexBuffer(buf, (n - 2) * 3, 1, 0, 0)
         return PolygonObj(vb, (float(bb[0]), float(bb[1]), 0.0), (float(bb[2]), float(bb[3]), 0.0),
-                          int(b.status.cpu().numpy()[0]) & 0xFFFFFFFF, int(b.ntri.cpu().numpy()[0]))
+                          int(st[0]), int(nt[0]))
 
 
 class Triangulation:

@@ -91,6 +91,8 @@ const mr_o_node* mr_o_tri_nodes(const mr_o_tri* t);
 int mr_o_polygon_batch(const mr_polygon_job* job, uint32_t* ids_out, int nthreads,
                        mr_o_stats* stats_total);
 void mr_o_palette(float rgb_out[12]);
+/* bench.py only: mean seconds per Polygon.create_polygon-shaped call (reusable arenas, one polygon), timed in C */
+double mr_o_time_create_polygon(const float* xy, uint32_t n, uint32_t offset, uint32_t prime, uint32_t reps);
 
 /* --- Terrain.zig ------------------------------------------------------------ */
 int mr_o_terrain_build(const mr_terrain_job* job, int nthreads);

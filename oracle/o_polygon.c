@@ -145,6 +145,43 @@ static void run_range(work* w) {
     mr_o_tri_destroy(t);
 }
 
+/* Timing helper for bench.py's single-polygon line: Polygon.create_polygon's own call shape -- one reusable
+ * Triangulation (Polygon.zig:18,116), one polygon per call, render_point writing GPUVertex into a mapped range --
+ * timed inside C so that no Python overhead is counted.  Returns the mean seconds per call. */
+#include <time.h>
+double mr_o_time_create_polygon(const float* xy, uint32_t n, uint32_t offset, uint32_t prime, uint32_t reps) {
+    mr_o_tri* t = mr_o_tri_new();
+    mr_layout L;
+    unsigned char* buf;
+    struct timespec a, b;
+    uint32_t r;
+    if (n < 3u || reps == 0u) return -1.0;
+    memset(&L, 0, sizeof(L));
+    L.stride = 32;
+    L.nattr = 2;
+    L.attr[0].offset = 0;
+    L.attr[0].ncomp = 2;
+    L.attr[1].offset = 16;
+    L.attr[1].ncomp = 3;
+    buf = (unsigned char*)calloc((size_t)(n - 2u) * 3u, 32);
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (r = 0; r < reps; ++r) {
+        sink s;
+        mr_o_unirand rng;
+        memset(&s, 0, sizeof(s));
+        s.base = buf;
+        s.cap = (n - 2u) * 3u;
+        s.L = &L;
+        mr_o_palette(s.pal);
+        mr_o_unirand_explicit(&rng, n, offset, prime);
+        (void)mr_o_tri_create_polygon(t, xy, n, rng, &s, render_point, NULL);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    free(buf);
+    mr_o_tri_destroy(t);
+    return ((double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec)) / (double)reps;
+}
+
 static void* thread_main(void* p) {
     run_range((work*)p);
     return NULL;

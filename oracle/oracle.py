@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
                                                  C.c_void_p]
         L.mr_o_test_lift_caps.restype = None
         L.mr_o_test_lift_caps.argtypes = [C.c_uint32]
+        L.mr_o_time_create_polygon.restype = C.c_double
+        L.mr_o_time_create_polygon.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.mr_o_hardware_threads.restype = C.c_int
         L.mr_o_tri_new.restype = C.c_void_p
         L.mr_o_tri_destroy.argtypes = [C.c_void_p]
@@ -265,6 +267,12 @@ def synth_polygons(seed, first_point, poly_index0=0, family=FAMILY_STAR) -> np.n
     xy = np.empty((npts, 2), dtype=np.float32)
     lib().mr_o_synth_polygons_family(family, seed, poly_index0, _ptr(first_point), len(first_point) - 1, _ptr(xy))
     return xy
+
+
+def time_create_polygon(xy, offset, prime, reps=20000) -> float:
+    """Mean seconds per single-polygon call of the CPU port (timed inside C)."""
+    xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+    return float(lib().mr_o_time_create_polygon(_ptr(xy), len(xy), offset, prime, reps))
 
 
 def lift_caps(multiplier: int):

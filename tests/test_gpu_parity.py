@@ -539,3 +539,186 @@ def test_polygon_offsets_device(ctx, oracle):
     ctx.check(ctx.lib.mr_polygon_offsets(ctx.handle, d.data_ptr(), 5000, out.data_ptr()), "offsets")
     ctx.sync()
     assert np.array_equal(out.cpu().numpy().view(np.uint64), oracle.polygon_offsets(fp))
+
+
+# ---- round 2 additions ---------------------------------------------------------------------------
+def test_synth_families_match_host_definition(ctx, oracle):
+    torch = _torch()
+    fp = oracle.synth_polygon_sizes(0x5EED0005, 400, 3, 1024, dist=1)
+    d = torch.from_numpy(fp.view(np.int64)).cuda()
+    for fam in (oracle.FAMILY_STAR, oracle.FAMILY_ELLIPSE, oracle.FAMILY_ZIPPER):
+        xy = torch.empty(int(fp[-1]) * 2, dtype=torch.float32, device="cuda")
+        ctx.check(ctx.lib.mr_synth_polygons_family(ctx.handle, fam, 0xFA111, 17, d.data_ptr(), 400, xy.data_ptr()), "synth")
+        ctx.sync()
+        want = oracle.synth_polygons(0xFA111, fp, poly_index0=17, family=fam)
+        assert np.array_equal(xy.cpu().numpy().view(np.uint32), want.reshape(-1).view(np.uint32)), fam
+
+
+@pytest.mark.parametrize("family", ["ellipse", "zipper"])
+def test_sound_families_every_size_class(ctx, oracle, family):
+    """The two families the reference triangulates correctly for every edge order (see
+    tests/test_reference_soundness_cpu.py), at and around every size-class boundary of the kernels, up to 1024
+    points: bit-exact and all status OK.  The zipper family is the non-convex one."""
+    fam = {"ellipse": oracle.FAMILY_ELLIPSE, "zipper": oracle.FAMILY_ZIPPER}[family]
+    sizes = []
+    for b in (64, 128, 168, 216, 288, 368, 504, 608, 768, 1024):
+        sizes += [b - 1, b, b + 1] if b < 1024 else [b - 1, b]
+    sizes = np.array(sizes * 6 + [3, 4, 5, 7, 8, 9, 31, 32, 33] * 4)
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    xy = oracle.synth_polygons(0x21BB, fp, family=fam)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=0x21BB)
+    assert (ref["status"] == 0).all()
+    tc = (C.c_uint32 * 8)()
+    ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
+    assert tc[6] == 0 and sum(tc[0:6]) == 0, list(tc)  # the first shared-memory pass handles all of them
+
+
+def test_zipper_loguniform_batch(ctx, oracle):
+    seed = 0x5EED0005
+    fp = oracle.synth_polygon_sizes(seed, 6000, 8, 1024, dist=1)
+    xy = oracle.synth_polygons(seed, fp, family=oracle.FAMILY_ZIPPER)
+    _, ref = _check_batch(ctx, oracle, xy, fp, seed=seed)
+    assert (ref["status"] == 0).all()
+
+
+def test_small_batch_path_single_polygon(ctx, oracle):
+    """Polygon.create_polygon's own call shape (Polygon.zig:81-107, App.zig:68-83): ONE polygon, every buffer in
+    host memory.  One kernel launch, results equal to the oracle, for every edge order of both App polygons."""
+    import myrenderer_b200 as mr
+
+    app = json.load(open(os.path.join(GOLDEN, "app_polygons.json")))
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    P = mr.Polygon(ctx)
+    for name in ("polygon1", "polygon2"):
+        p = np.array(app[name], dtype=np.float32)
+        n = len(p)
+        fp = np.array([0, n], dtype=np.uint64)
+        ft = np.array([0, n - 2], dtype=np.uint64)
+        for key, want in kat[name].items():
+            op = np.array([int(x) for x in key.split(",")], dtype=np.uint32)
+            vtx = np.full((n - 2) * 96, 0xCD, dtype=np.uint8)
+            bbox = np.zeros(4, dtype=np.float32)
+            st = np.full(1, 77, dtype=np.uint32)
+            nt = np.zeros(1, dtype=np.uint32)
+            l0 = ctx.launch_count
+            P.triangulate(P.job(p, fp, 1, vtx_out=vtx, first_tri=ft, bbox_out=bbox, status_out=st, ntri_out=nt, offset_prime=op))
+            assert ctx.launch_count - l0 == 1, "the single-polygon call must be one kernel launch"
+            assert int(st[0]) == want["status"] and int(nt[0]) == n - 2
+            assert hashlib.sha256(vtx.tobytes()).hexdigest() == want["vtx_sha256"]
+            assert bbox.view(np.uint32).tolist() == want["bbox_bits"]
+
+
+def test_small_batch_path_mixed(ctx, oracle):
+    """Small host-memory batches through the one-block path: every size class incl. > 1024 points, degenerate and
+    too-large polygons, exploding stars (which need the retry tiers), seeded and explicit edge orders, optional
+    outputs left out, sub-ranges with point_base / tri_base."""
+    import myrenderer_b200 as mr
+
+    P = mr.Polygon(ctx)
+    seed = 0xBEEF
+    sizes = np.array([7, 4, 2, 3, 64, 65, 130, 300, 520, 700, 1024, 1500, 36, 36, 5000, 12, 0, 1, 900, 450])
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    for fam in (oracle.FAMILY_STAR, oracle.FAMILY_ZIPPER):
+        xy = oracle.synth_polygons(seed, fp, family=fam)
+        ref = oracle.polygon_batch(xy, fp, seed=seed, nthreads=0)
+        ft = ref["first_tri"]
+        npoly = len(sizes)
+        vtx = np.full(max(int(ft[-1]) * 96, 1), 0xEE, dtype=np.uint8)
+        st = np.zeros(npoly, dtype=np.uint32)
+        nt = np.zeros(npoly, dtype=np.uint32)
+        bbox = np.zeros((npoly, 4), dtype=np.float32)
+        P.triangulate(P.job(xy, fp, npoly, vtx_out=vtx, first_tri=ft, bbox_out=bbox, status_out=st, ntri_out=nt, seed=seed))
+        assert np.array_equal(st, ref["status"]), (st, ref["status"])
+        assert np.array_equal(nt, ref["ntri"]) and np.array_equal(vtx[: int(ft[-1]) * 96], ref["vtx"])
+        assert np.array_equal(bbox.view(np.uint32), ref["bbox"].view(np.uint32))
+        # sub-range [5, 12) into the same buffers, only the vertex output requested
+        vtx2 = np.full_like(vtx, 0x11)
+        P.triangulate(P.job(xy, fp[5:13].copy(), 7, vtx_out=vtx2, first_tri=ft[5:13].copy(), seed=seed, poly_index0=5))
+        a, z = int(ft[5]) * 96, int(ft[12]) * 96
+        assert np.array_equal(vtx2[a:z], ref["vtx"][a:z])
+        assert (vtx2[:a] == 0x11).all() and (vtx2[z:] == 0x11).all()  # nothing outside the job's range is touched
+
+
+def test_pinned_vertex_output_without_other_host_outputs(ctx, oracle):
+    """a pinned host vtx_out is written by the kernels directly; the call must not return before they
+    are done even when no other host output forces a copy-back."""
+    import myrenderer_b200 as mr
+
+    torch = _torch()
+    seed = 34
+    fp = oracle.synth_polygon_sizes(seed, 20000, 8, 64)
+    xy = oracle.synth_polygons(seed, fp)
+    ref = oracle.polygon_batch(xy, fp, seed=seed, nthreads=0, want_ids=False)
+    ft = ref["first_tri"]
+    P = mr.Polygon(ctx)
+    xy_d = torch.from_numpy(xy).cuda()
+    fp_d = torch.from_numpy(fp.view(np.int64)).cuda()
+    ft_d = torch.from_numpy(ft.view(np.int64)).cuda()
+    st_d = torch.empty(20000, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        pinned = torch.full((int(ft[-1]) * 96,), 0xAB, dtype=torch.uint8).pin_memory()
+        P.triangulate(P.job(xy_d, fp_d, 20000, vtx_out=pinned, first_tri=ft_d, status_out=st_d, seed=seed))
+        got = pinned.numpy().copy()  # no ctx.sync(): the call itself must have waited
+        assert np.array_equal(got, ref["vtx"])
+
+
+def test_argument_validation_alignment_and_empty_bands(ctx, oracle):
+    import myrenderer_b200 as mr
+
+    torch = _torch()
+    n = 64
+    h = torch.from_numpy(oracle.synth_heightmap_u16(1, n).view(np.int16)).cuda()
+    T = mr.Terrain(ctx)
+    vtx = torch.empty(n * n * 32 + 64, dtype=torch.uint8, device="cuda")
+    idx = torch.empty(6 * (n - 1) * (n - 1) + 16, dtype=torch.int32, device="cuda")
+    with pytest.raises(mr.MrError):  # idx_out off by one u32: would fault in the 8-byte stores
+        T.build(T.job(h, n, vtx_out=vtx, idx_out=idx.data_ptr() + 4))
+    with pytest.raises(mr.MrError):
+        T.build(T.job(h, n, vtx_out=vtx.data_ptr() + 2, idx_out=idx))
+    with pytest.raises(mr.MrError):  # vtx_row0 beyond the (empty) band: used to wrap into a huge allocation
+        T.build(T.job(h, n, rows=(3, 3), vtx_out=np.zeros(16, dtype=np.uint8), vtx_row0=9))
+    T.build(T.job(h, n, rows=(5, 5), qrows=(2, 2), vtx_out=vtx, idx_out=idx))  # empty band: a no-op
+    T.build(T.job(h, n, vtx_out=vtx, idx_out=idx))
+    ctx.sync()  # the context is still healthy
+    ovtx, oidx = oracle.terrain_build(h.cpu().numpy().view(np.uint16).reshape(n, n), n)
+    assert np.array_equal(vtx.cpu().numpy()[: n * n * 32], ovtx)
+    assert np.array_equal(idx.cpu().numpy().view(np.uint32)[: len(oidx)], oidx)
+
+
+def test_context_trim_releases_scratch(ctx, oracle):
+    n = 512
+    h = oracle.synth_heightmap_u16(3, n)
+    import myrenderer_b200 as mr
+
+    T = mr.Terrain(ctx)
+    vtx = np.zeros(n * n * 32, dtype=np.uint8)
+    idx = np.zeros(6 * (n - 1) * (n - 1), dtype=np.uint32)
+    T.build(T.job(h, n, vtx_out=vtx, idx_out=idx))
+    b = C.c_uint64()
+    ctx.check(ctx.lib.mr_context_scratch_bytes(ctx.handle, C.byref(b)), "scratch bytes")
+    assert b.value >= n * n * 32
+    ctx.check(ctx.lib.mr_context_trim(ctx.handle), "trim")
+    ctx.check(ctx.lib.mr_context_scratch_bytes(ctx.handle, C.byref(b)), "scratch bytes")
+    assert b.value == 0
+    vtx2 = np.zeros_like(vtx)
+    T.build(T.job(h, n, vtx_out=vtx2, idx_out=idx))  # and it works again afterwards
+    assert np.array_equal(vtx, vtx2)
+    ovtx, oidx = oracle.terrain_build(h, n)
+    assert np.array_equal(vtx, ovtx) and np.array_equal(idx, oidx)
+
+
+def test_terrain_host_band_into_larger_buffer(ctx, oracle):
+    """Host vtx_out / idx_out with vtx_row0 / idx_qrow0 below the band: only the band's bytes are written."""
+    import myrenderer_b200 as mr
+
+    n = 200
+    h = oracle.synth_heightmap_u16(5, n)
+    T = mr.Terrain(ctx)
+    vtx = np.full(n * n * 32, 0x5A, dtype=np.uint8)
+    idx = np.full(6 * (n - 1) * (n - 1), 0x5A5A5A5A, dtype=np.uint32)
+    T.build(T.job(h, n, rows=(50, 120), qrows=(40, 90), vtx_out=vtx, vtx_row0=0, idx_out=idx, idx_qrow0=0))
+    ovtx, oidx = oracle.terrain_build(h, n)
+    a, z = 50 * n * 32, 120 * n * 32
+    assert np.array_equal(vtx[a:z], ovtx[a:z]) and (vtx[:a] == 0x5A).all() and (vtx[z:] == 0x5A).all()
+    a, z = 40 * 6 * (n - 1), 90 * 6 * (n - 1)
+    assert np.array_equal(idx[a:z], oidx[a:z]) and (idx[:a] == 0x5A5A5A5A).all() and (idx[z:] == 0x5A5A5A5A).all()
