@@ -209,6 +209,40 @@ int mr_selftest_fastdiv(mr_context* ctx, float divisor, int force_fast, uint64_t
 /* Standalone heightmap normalisation (Terrain.zig:114-124): u16 -> f32. */
 int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, float* out);
 
+/* ---- terrain tiles and culling -----------------------------
+ * The mesh is cut into tiles of tile_rows x tile_cols QUADS (the last tile of a row / column may be
+ * smaller); tile t = tr * tiles_c + tc covers quad rows [tr*tile_rows, ...) and quad columns
+ * [tc*tile_cols, ...), i.e. vertex rows r0..r1 and columns c0..c1 INCLUSIVE with r1 = last quad row + 1.
+ *
+ * mr_terrain_tile_bounds writes one bounding box per tile in the form SceneNode keeps them
+ * (SceneNode.zig:11-22, Terrain.zig:103-110 per tile instead of per terrain): 8 floats
+ *     p0 = (min x, min y, min z, 1)   p1 = (max x, max y, max z, 1)
+ * over the tile's vertices, positions as defined for mr_terrain_build (x from the row, z from the
+ * column, y = height_scale * h).  min/max are exact (comparisons only), so the boxes are bit-exact.
+ *
+ * mr_terrain_cull applies the reference's visibility test (SceneNode.zig:96-110) to every tile box:
+ *     q0 = M * p0 unless some component of p0 is -inf;  q1 = M * p1 unless some component of p1 is +inf
+ *     visible = all(q1 > 0) or all(q0 < 1)                                (all four components, no divide)
+ * with M the composed transform as the memory image of mach.math.Mat4x4 (four column Vec4s:
+ * xform[4*col + row]) and M * p evaluated like mach's Mat4x4.mulVec: result[i] starts at 0 and adds
+ * xform[4*j + i] * p[j] for j = 0..3 in order, every operation separately rounded.  (mach is not
+ * vendored in the reference tree: mulVec is restated from the mach source -- parity unpinned.)
+ * Outputs, each optional (NULL to skip), device or host pointers:
+ *     visible_out[t]      1 / 0 per tile
+ *     visible_ids_out[k]  the visible tiles in ascending order, k < counts_out[0]
+ *     idx_out             compacted index buffer: the visible tiles in ascending order, each tile's quads
+ *                         row-major, six indices per quad exactly as mr_terrain_build writes them --
+ *                         one drawIndexed(counts_out[1]) draws what survives the cull
+ *     counts_out[2]       {visible tiles, indices written} as uint64 */
+int mr_terrain_tile_count(uint32_t n, uint32_t tile_rows, uint32_t tile_cols, uint32_t* tiles_r_out,
+                          uint32_t* tiles_c_out);
+int mr_terrain_tile_bounds(mr_context* ctx, const void* height, uint32_t height_fmt, uint32_t n,
+                           uint32_t tile_rows, uint32_t tile_cols, const mr_terrain_params* params,
+                           float* bbox_out /* tiles * 8 */);
+int mr_terrain_cull(mr_context* ctx, const float* bbox /* tiles * 8 */, uint32_t n, uint32_t tile_rows,
+                    uint32_t tile_cols, const float xform[16], uint32_t* visible_out,
+                    uint32_t* visible_ids_out, uint32_t* idx_out, uint64_t* counts_out);
+
 /* ---- polygons --------------------------------------------------------------
  * Triangulates npoly polygons exactly as Triangulation.create_polygon would,
  * one after the other, with render_point as the emit sink.

@@ -154,6 +154,12 @@ SIGNATURES = {
         [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "mr_synth_polygons": (
         C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "mr_terrain_tile_count": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mr_terrain_tile_bounds": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "mr_terrain_cull": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_void_p]),
     "mr_context_trim": (C.c_int, [C.c_void_p]),
     "mr_context_scratch_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "mr_synth_polygons_family": (

@@ -7,6 +7,11 @@
 #include "unirand.cuh"
 
 int mr_heightmap_normalize_impl(mr_context* ctx, const uint16_t* in, uint64_t count, float* out);
+int mr_terrain_tile_bounds_impl(mr_context* ctx, const void* height_dev, uint32_t height_fmt, uint32_t n, uint32_t tile_rows,
+                                uint32_t tile_cols, const mr_terrain_params* p, float* bbox_dev);
+int mr_terrain_cull_impl(mr_context* ctx, const float* bbox_dev, uint32_t n, uint32_t tile_rows, uint32_t tile_cols,
+                         const float xform[16], uint32_t* visible_dev, uint32_t* ids_dev, unsigned long long* first_index_dev,
+                         uint32_t* idx_dev, unsigned long long* counts_dev);
 int mr_selftest_fastdiv_impl(mr_context* ctx, float b, int force_fast, unsigned long long* mismatches_dev);
 int mr_polygon_offsets_impl(mr_context* ctx, const uint64_t* first_point_dev, uint32_t npoly, uint64_t* first_tri_dev);
 int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]);
@@ -345,6 +350,81 @@ int mr_terrain_build_full(mr_context* ctx, const void* height, uint32_t height_f
     if (layout) j.layout = *layout; else mr_layout_preset(MR_LAYOUT_TERRAINVERTEX, &j.layout);
     if (params) j.params = *params; else mr_terrain_params_default(&j.params);
     return mr_terrain_build(ctx, &j);
+}
+
+int mr_terrain_tile_count(uint32_t n, uint32_t tile_rows, uint32_t tile_cols, uint32_t* tiles_r_out, uint32_t* tiles_c_out) {
+    if (n < 2 || tile_rows == 0 || tile_cols == 0) return MR_E_BADARG;
+    if (tiles_r_out) *tiles_r_out = (n - 1u + tile_rows - 1u) / tile_rows;
+    if (tiles_c_out) *tiles_c_out = (n - 1u + tile_cols - 1u) / tile_cols;
+    return MR_OK;
+}
+
+int mr_terrain_tile_bounds(mr_context* ctx, const void* height, uint32_t height_fmt, uint32_t n, uint32_t tile_rows,
+                           uint32_t tile_cols, const mr_terrain_params* params, float* bbox_out) {
+    if (!ctx || !height || !bbox_out) return MR_E_BADARG;
+    uint32_t tr = 0, tc = 0;
+    if (n > 65535u || mr_terrain_tile_count(n, tile_rows, tile_cols, &tr, &tc) != MR_OK) return mr_fail(ctx, MR_E_BADARG, "tiles: bad n or tile size");
+    if (height_fmt != MR_HEIGHT_U16 && height_fmt != MR_HEIGHT_F32) return mr_fail(ctx, MR_E_BADARG, "tiles: bad height_fmt");
+    if (reinterpret_cast<uintptr_t>(bbox_out) & 15u) return mr_fail(ctx, MR_E_BADARG, "tiles: bbox_out must be 16-byte aligned");
+    mr_terrain_params p;
+    if (params) p = *params; else mr_terrain_params_default(&p);
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* hdev = nullptr;
+    int rc = mr_stage_in(ctx, 0, height, (size_t)n * n * (height_fmt == MR_HEIGHT_U16 ? 2 : 4), &hdev);
+    if (rc) return rc;
+    void* bdev = nullptr;
+    bool st = false;
+    const size_t bytes = (size_t)tr * tc * 32;
+    rc = mr_stage_out(ctx, 4, bbox_out, bytes, &bdev, &st);
+    if (rc) return rc;
+    rc = mr_terrain_tile_bounds_impl(ctx, hdev, height_fmt, n, tile_rows, tile_cols, &p, static_cast<float*>(bdev));
+    if (rc) return rc;
+    if (st) {
+        rc = mr_copy_back(ctx, bbox_out, bdev, bytes);
+        if (rc) return rc;
+    }
+    return mr_finish_host_io(ctx);
+}
+
+int mr_terrain_cull(mr_context* ctx, const float* bbox, uint32_t n, uint32_t tile_rows, uint32_t tile_cols, const float xform[16],
+                    uint32_t* visible_out, uint32_t* visible_ids_out, uint32_t* idx_out, uint64_t* counts_out) {
+    if (!ctx || !bbox || !xform) return MR_E_BADARG;
+    uint32_t tr = 0, tc = 0;
+    if (n > 65535u || mr_terrain_tile_count(n, tile_rows, tile_cols, &tr, &tc) != MR_OK) return mr_fail(ctx, MR_E_BADARG, "cull: bad n or tile size");
+    if (idx_out && (reinterpret_cast<uintptr_t>(idx_out) & 7u)) return mr_fail(ctx, MR_E_BADARG, "cull: idx_out must be 8-byte aligned");
+    const size_t ntiles = (size_t)tr * tc;
+    MR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void* bdev = nullptr;
+    int rc = mr_stage_in(ctx, 0, bbox, ntiles * 32, &bdev);
+    if (rc) return rc;
+    void *vdev = nullptr, *idev = nullptr, *xdev = nullptr, *cdev = nullptr, *work = nullptr;
+    bool sv = false, si = false, sx = false, sc = false;
+    if (visible_out) { rc = mr_stage_out(ctx, 1, visible_out, ntiles * 4, &vdev, &sv); if (rc) return rc; }
+    // visible ids and per-slot first index are needed internally even when the caller does not ask for the ids
+    rc = mr_scratch(ctx, 10, ntiles * 12 + 16, &work);
+    if (rc) return rc;
+    unsigned long long* first_index = static_cast<unsigned long long*>(work);
+    uint32_t* ids_scratch = reinterpret_cast<uint32_t*>(first_index + ntiles);
+    if (visible_ids_out) { rc = mr_stage_out(ctx, 2, visible_ids_out, ntiles * 4, &idev, &si); if (rc) return rc; }
+    else idev = ids_scratch;
+    const size_t max_idx_bytes = 24ull * (size_t)(n - 1u) * (n - 1u);
+    if (idx_out) { rc = mr_stage_out(ctx, 5, idx_out, max_idx_bytes, &xdev, &sx); if (rc) return rc; }
+    if (counts_out) { rc = mr_stage_out(ctx, 3, counts_out, 16, &cdev, &sc); if (rc) return rc; }
+    else { rc = mr_scratch(ctx, 3, 16, &cdev); if (rc) return rc; }
+    rc = mr_terrain_cull_impl(ctx, static_cast<const float*>(bdev), n, tile_rows, tile_cols, xform, static_cast<uint32_t*>(vdev),
+                              static_cast<uint32_t*>(idev), first_index, static_cast<uint32_t*>(xdev),
+                              static_cast<unsigned long long*>(cdev));
+    if (rc) return rc;
+    if (sv) { rc = mr_copy_back(ctx, visible_out, vdev, ntiles * 4); if (rc) return rc; }
+    uint64_t counts[2] = {0, 0};
+    if (si || sx || sc) {  // host outputs: only the filled prefixes travel
+        MR_CUDA(ctx, cudaMemcpyAsync(counts, cdev, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        MR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (sc) memcpy(counts_out, counts, 16);
+        if (si && counts[0]) { rc = mr_copy_back(ctx, visible_ids_out, idev, (size_t)counts[0] * 4); if (rc) return rc; }
+        if (sx && counts[1]) { rc = mr_copy_back(ctx, idx_out, xdev, (size_t)counts[1] * 4); if (rc) return rc; }
+    }
+    return mr_finish_host_io(ctx);
 }
 
 int mr_selftest_fastdiv(mr_context* ctx, float divisor, int force_fast, uint64_t* mismatches_out) {

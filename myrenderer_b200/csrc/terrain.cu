@@ -260,6 +260,184 @@ __global__ void __launch_bounds__(256) heightmap_normalize_k(const uint16_t* __r
     for (; i < count; i += step) out[i] = height_from_u16(__ldg(in + i));
 }
 
+// ---- tiles and culling --------------------------------------------------------
+// Tile bounding boxes: one CTA per tile reduces the heights of the tile's (rows+1) x (cols+1) vertices to their
+// minimum and maximum (comparisons only: exact) and writes p0 / p1 as SceneNode keeps them.  Read-only, 2 B per
+// texel for a u16 map.
+struct TileArgs {
+    const void* height;
+    uint32_t n, tile_rows, tile_cols, tiles_c;
+    float grid_step, origin_scale, height_scale;
+    float* bbox_out;
+};
+
+template <bool U16>
+__global__ void __launch_bounds__(256) terrain_tile_bounds_k(const TileArgs a) {
+    const uint32_t t = blockIdx.x;
+    const uint32_t tr = t / a.tiles_c, tc = t - tr * a.tiles_c;
+    const uint32_t r0 = tr * a.tile_rows, c0 = tc * a.tile_cols;
+    const uint32_t r1 = min(r0 + a.tile_rows, a.n - 1u), c1 = min(c0 + a.tile_cols, a.n - 1u);  // inclusive vertex range
+    const uint32_t w = c1 - c0 + 1u, h = r1 - r0 + 1u;
+    float lo = __uint_as_float(0x7F800000u), hi = __uint_as_float(0xFF800000u);
+    for (uint32_t i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const uint32_t rr = i / w, cc = i - rr * w;
+        const float v = load_height<U16>(a.height, (size_t)(r0 + rr) * a.n + c0 + cc);
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float ol = __shfl_xor_sync(0xFFFFFFFFu, lo, d), oh = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+        lo = ol < lo ? ol : lo;
+        hi = oh > hi ? oh : hi;
+    }
+    __shared__ float slo[8], shi[8];
+    if ((threadIdx.x & 31u) == 0) {
+        slo[threadIdx.x >> 5] = lo;
+        shi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            lo = slo[k] < lo ? slo[k] : lo;
+            hi = shi[k] > hi ? shi[k] : hi;
+        }
+        const float org = __fmul_rn(a.origin_scale, (float)a.n);
+        const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
+        const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
+        const float ya = __fmul_rn(a.height_scale, lo), yb = __fmul_rn(a.height_scale, hi);
+        float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * (size_t)t);
+        o[0] = make_float4(fminf(xa, xb), fminf(ya, yb), fminf(za, zb), 1.0f);
+        o[1] = make_float4(fmaxf(xa, xb), fmaxf(ya, yb), fmaxf(za, zb), 1.0f);
+    }
+}
+
+// mach.math Mat4x4.mulVec: result[i] = 0; for j in 0..3: result[i] += m[j][i] * v[j]   (every operation rounded)
+__device__ __forceinline__ float4 mach_mul_vec(const float* m, const float4 v) {
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = __fadd_rn(acc, __fmul_rn(m[4 * j + i], vv[j]));
+        r[i] = acc;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+struct CullArgs {
+    const float* bbox;
+    uint32_t ntiles, n, tile_rows, tile_cols, tiles_c;
+    float m[16];
+    uint32_t* visible_out;      // optional
+    uint32_t* visible_ids;      // ntiles (scratch or the caller's)
+    unsigned long long* first_index;  // ntiles: first index-buffer word of visible slot k (scratch)
+    unsigned long long* counts;       // [0] visible tiles, [1] indices
+};
+
+// SceneNode.zig:96-110 per tile, then an ordered compaction.  One CTA of 1024 threads walks the tiles in chunks
+// (a terrain has at most a few 10^4 tiles); the order of the visible list is the tile order.
+__global__ void __launch_bounds__(1024) terrain_cull_k(const CullArgs a) {
+    __shared__ uint32_t wsum_t[32];
+    __shared__ unsigned long long wsum_q[32];
+    __shared__ uint32_t base_t;
+    __shared__ unsigned long long base_q;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        base_t = 0;
+        base_q = 0;
+    }
+    __syncthreads();
+    const float inf = __uint_as_float(0x7F800000u);
+    for (uint32_t t0 = 0; t0 < a.ntiles; t0 += 1024) {
+        const uint32_t t = t0 + threadIdx.x;
+        bool vis = false;
+        uint32_t quads = 0;
+        if (t < a.ntiles) {
+            float4 p0 = *reinterpret_cast<const float4*>(a.bbox + 8 * (size_t)t);
+            float4 p1 = *reinterpret_cast<const float4*>(a.bbox + 8 * (size_t)t + 4);
+            if (fminf(fminf(p0.x, p0.y), fminf(p0.z, p0.w)) != -inf) p0 = mach_mul_vec(a.m, p0);  // :100-101
+            if (fmaxf(fmaxf(p1.x, p1.y), fmaxf(p1.z, p1.w)) != inf) p1 = mach_mul_vec(a.m, p1);   // :103-105
+            vis = (p1.x > 0.0f && p1.y > 0.0f && p1.z > 0.0f && p1.w > 0.0f) ||
+                  (p0.x < 1.0f && p0.y < 1.0f && p0.z < 1.0f && p0.w < 1.0f);  // :111
+            const uint32_t tr = t / a.tiles_c, tc = t - tr * a.tiles_c;
+            const uint32_t qr = min(a.tile_rows, a.n - 1u - tr * a.tile_rows), qc = min(a.tile_cols, a.n - 1u - tc * a.tile_cols);
+            quads = vis ? qr * qc : 0u;
+            if (a.visible_out) a.visible_out[t] = vis ? 1u : 0u;
+        }
+        // block-wide exclusive scan of (visible, quads) in thread order
+        uint32_t it = vis ? 1u : 0u;
+        unsigned long long iq = quads;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ot = __shfl_up_sync(0xFFFFFFFFu, it, d);
+            const unsigned long long oq = __shfl_up_sync(0xFFFFFFFFu, iq, d);
+            if ((int)lane >= d) {
+                it += ot;
+                iq += oq;
+            }
+        }
+        if (lane == 31) {
+            wsum_t[warp] = it;
+            wsum_q[warp] = iq;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t st = wsum_t[lane];
+            unsigned long long sq = wsum_q[lane];
+            const uint32_t st0 = st;
+            const unsigned long long sq0 = sq;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t ot = __shfl_up_sync(0xFFFFFFFFu, st, d);
+                const unsigned long long oq = __shfl_up_sync(0xFFFFFFFFu, sq, d);
+                if ((int)lane >= d) {
+                    st += ot;
+                    sq += oq;
+                }
+            }
+            wsum_t[lane] = st - st0;  // exclusive over warps
+            wsum_q[lane] = sq - sq0;
+        }
+        __syncthreads();
+        const uint32_t slot = base_t + wsum_t[warp] + it - (vis ? 1u : 0u);
+        const unsigned long long firstq = base_q + wsum_q[warp] + iq - quads;
+        if (vis) {
+            a.visible_ids[slot] = t;
+            a.first_index[slot] = firstq * 6ull;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            base_t += wsum_t[31] + it;
+            base_q += wsum_q[31] + iq;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.counts[0] = base_t;
+        a.counts[1] = base_q * 6ull;
+    }
+}
+
+// compacted index buffer: CTA k writes visible tile k (CTAs beyond the visible count leave at once)
+__global__ void __launch_bounds__(256) terrain_cull_indices_k(const CullArgs a, uint32_t* __restrict__ idx_out) {
+    if (blockIdx.x >= a.counts[0]) return;
+    const uint32_t t = a.visible_ids[blockIdx.x];
+    const uint32_t tr = t / a.tiles_c, tc = t - tr * a.tiles_c;
+    const uint32_t r0 = tr * a.tile_rows, c0 = tc * a.tile_cols;
+    const uint32_t qr = min(a.tile_rows, a.n - 1u - r0), qc = min(a.tile_cols, a.n - 1u - c0);
+    uint2* dst = reinterpret_cast<uint2*>(idx_out + a.first_index[blockIdx.x]);  // 24-byte quads: 8-byte aligned
+    const uint32_t n = a.n;
+    for (uint32_t q = threadIdx.x; q < qr * qc; q += blockDim.x) {
+        const uint32_t lr = q / qc, lc = q - lr * qc;
+        const uint32_t i00 = (r0 + lr) * n + c0 + lc;
+        dst[3 * (size_t)q] = make_uint2(i00 + n, i00);
+        dst[3 * (size_t)q + 1] = make_uint2(i00 + n + 1, i00 + n + 1);
+        dst[3 * (size_t)q + 2] = make_uint2(i00, i00 + 1);
+    }
+}
+
 // exhaustive check of div_const against __fdiv_rn over all 2^32 dividends
 __global__ void __launch_bounds__(256) selftest_fastdiv_k(DivConst c, unsigned long long* mismatches) {
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
@@ -356,5 +534,52 @@ int mr_selftest_fastdiv_impl(mr_context* ctx, float b, int force_fast, unsigned 
     if (force_fast) c.fast = 1;
     selftest_fastdiv_k<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c, mismatches_dev);
     MR_LAUNCH_CHECK(ctx, "selftest_fastdiv_k");
+    return MR_OK;
+}
+
+int mr_terrain_tile_bounds_impl(mr_context* ctx, const void* height_dev, uint32_t height_fmt, uint32_t n, uint32_t tile_rows,
+                                uint32_t tile_cols, const mr_terrain_params* p, float* bbox_dev) {
+    TileArgs a;
+    a.height = height_dev;
+    a.n = n;
+    a.tile_rows = tile_rows;
+    a.tile_cols = tile_cols;
+    const uint32_t tiles_r = (n - 1u + tile_rows - 1u) / tile_rows;
+    a.tiles_c = (n - 1u + tile_cols - 1u) / tile_cols;
+    a.grid_step = p->grid_step;
+    a.origin_scale = p->origin_scale;
+    a.height_scale = p->height_scale;
+    a.bbox_out = bbox_dev;
+    const unsigned grid = tiles_r * a.tiles_c;
+    if (height_fmt == MR_HEIGHT_U16)
+        terrain_tile_bounds_k<true><<<grid, 256, 0, ctx->stream>>>(a);
+    else
+        terrain_tile_bounds_k<false><<<grid, 256, 0, ctx->stream>>>(a);
+    MR_LAUNCH_CHECK(ctx, "terrain_tile_bounds_k");
+    return MR_OK;
+}
+
+int mr_terrain_cull_impl(mr_context* ctx, const float* bbox_dev, uint32_t n, uint32_t tile_rows, uint32_t tile_cols,
+                         const float xform[16], uint32_t* visible_dev, uint32_t* ids_dev, unsigned long long* first_index_dev,
+                         uint32_t* idx_dev, unsigned long long* counts_dev) {
+    CullArgs a;
+    a.bbox = bbox_dev;
+    a.n = n;
+    a.tile_rows = tile_rows;
+    a.tile_cols = tile_cols;
+    const uint32_t tiles_r = (n - 1u + tile_rows - 1u) / tile_rows;
+    a.tiles_c = (n - 1u + tile_cols - 1u) / tile_cols;
+    a.ntiles = tiles_r * a.tiles_c;
+    memcpy(a.m, xform, sizeof(a.m));
+    a.visible_out = visible_dev;
+    a.visible_ids = ids_dev;
+    a.first_index = first_index_dev;
+    a.counts = counts_dev;
+    terrain_cull_k<<<1, 1024, 0, ctx->stream>>>(a);
+    MR_LAUNCH_CHECK(ctx, "terrain_cull_k");
+    if (idx_dev) {
+        terrain_cull_indices_k<<<a.ntiles, 256, 0, ctx->stream>>>(a, idx_dev);
+        MR_LAUNCH_CHECK(ctx, "terrain_cull_indices_k");
+    }
     return MR_OK;
 }

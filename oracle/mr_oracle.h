@@ -103,6 +103,14 @@ void mr_o_heightmap_normalize(const uint16_t* in, uint64_t count, float* out);
 int mr_o_terrain_shader_vertex(const float* h, uint32_t n, uint64_t vi,
                                const mr_terrain_params* p, float out4[4]);
 
+/* tiles + culling: same contracts as mr_terrain_tile_bounds / mr_terrain_cull with host pointers; the visibility
+ * test is SceneNode.zig:96-110 (mr_o_scene_node_should_render is the per-box form) */
+int mr_o_terrain_tile_bounds(const void* height, uint32_t fmt, uint32_t n, uint32_t tile_rows, uint32_t tile_cols,
+                             const mr_terrain_params* p, float* bbox_out);
+int mr_o_scene_node_should_render(const float xform[16], const float p0[4], const float p1[4]);
+int mr_o_terrain_cull(const float* bbox, uint32_t n, uint32_t tile_rows, uint32_t tile_cols, const float xform[16],
+                      uint32_t* visible_out, uint32_t* visible_ids_out, uint32_t* idx_out, uint64_t counts_out[2]);
+
 /* --- synthetic inputs (same definitions as the library's generators) -------- */
 void mr_o_synth_heightmap_u16(uint64_t seed, uint32_t n, uint32_t row0, uint32_t rows,
                               uint16_t* out);

@@ -146,3 +146,102 @@ int mr_o_terrain_build(const mr_terrain_job* j, int nthreads) {
     free(th);
     return MR_OK;
 }
+
+/* ---- tiles and culling ---------------------------------------------------
+ * Tile boxes: Terrain.zig:103-110 computes ONE box for the terrain, (-bound,0,-bound)..(bound,5,bound); here the
+ * same kind of box per tile, tight in y (NEW SPEC: the reference does not tile).
+ * Visibility: SceneNode.zig:96-110, statement for statement, with mach.math.Mat4x4.mulVec restated from the mach
+ * source (mach is not vendored under /root/reference: PARITY UNPINNED for mulVec's evaluation order). */
+static void mach_mul_vec(const float m[16], const float v[4], float out[4]) {
+    int i, j;
+    for (i = 0; i < 4; ++i) {
+        float acc = 0.0f;
+        for (j = 0; j < 4; ++j) acc = acc + m[4 * j + i] * v[j]; /* result[i] += matrix.v[j].v[i] * vector.v[j] */
+        out[i] = acc;
+    }
+}
+
+static float texel_full(const void* height, uint32_t fmt, uint32_t n, uint32_t r, uint32_t c) {
+    size_t idx = (size_t)r * n + c;
+    if (fmt == MR_HEIGHT_U16) return norm_u16(((const uint16_t*)height)[idx]);
+    return ((const float*)height)[idx];
+}
+
+int mr_o_terrain_tile_bounds(const void* height, uint32_t fmt, uint32_t n, uint32_t tile_rows, uint32_t tile_cols,
+                             const mr_terrain_params* p, float* bbox_out) {
+    uint32_t tiles_r, tiles_c, tr, tc;
+    if (!height || !bbox_out || n < 2 || !tile_rows || !tile_cols) return MR_E_BADARG;
+    tiles_r = (n - 1u + tile_rows - 1u) / tile_rows;
+    tiles_c = (n - 1u + tile_cols - 1u) / tile_cols;
+    for (tr = 0; tr < tiles_r; ++tr)
+        for (tc = 0; tc < tiles_c; ++tc) {
+            uint32_t r0 = tr * tile_rows, c0 = tc * tile_cols, r, c;
+            uint32_t r1 = r0 + tile_rows < n - 1u ? r0 + tile_rows : n - 1u;
+            uint32_t c1 = c0 + tile_cols < n - 1u ? c0 + tile_cols : n - 1u;
+            float lo = INFINITY, hi = -INFINITY, org = p->origin_scale * (float)n;
+            float xa, xb, za, zb, ya, yb;
+            float* o = bbox_out + 8u * ((size_t)tr * tiles_c + tc);
+            for (r = r0; r <= r1; ++r)
+                for (c = c0; c <= c1; ++c) {
+                    float v = texel_full(height, fmt, n, r, c);
+                    if (v < lo) lo = v;
+                    if (v > hi) hi = v;
+                }
+            xa = p->grid_step * (float)r0 - org;
+            xb = p->grid_step * (float)r1 - org;
+            za = p->grid_step * (float)c0 - org;
+            zb = p->grid_step * (float)c1 - org;
+            ya = p->height_scale * lo;
+            yb = p->height_scale * hi;
+            o[0] = fminf(xa, xb); o[1] = fminf(ya, yb); o[2] = fminf(za, zb); o[3] = 1.0f;
+            o[4] = fmaxf(xa, xb); o[5] = fmaxf(ya, yb); o[6] = fmaxf(za, zb); o[7] = 1.0f;
+        }
+    return MR_OK;
+}
+
+/* SceneNode.zig:96-110 for one box: returns should_render */
+int mr_o_scene_node_should_render(const float xform[16], const float p0_in[4], const float p1_in[4]) {
+    float p0[4], p1[4];
+    float mn = fminf(fminf(p0_in[0], p0_in[1]), fminf(p0_in[2], p0_in[3]));
+    float mx = fmaxf(fmaxf(p1_in[0], p1_in[1]), fmaxf(p1_in[2], p1_in[3]));
+    memcpy(p0, p0_in, 16);
+    memcpy(p1, p1_in, 16);
+    if (mn != -INFINITY) mach_mul_vec(xform, p0_in, p0); /* :99-101 */
+    if (mx != INFINITY) mach_mul_vec(xform, p1_in, p1);  /* :103-105 */
+    return (p1[0] > 0.0f && p1[1] > 0.0f && p1[2] > 0.0f && p1[3] > 0.0f) ||
+           (p0[0] < 1.0f && p0[1] < 1.0f && p0[2] < 1.0f && p0[3] < 1.0f); /* :111 */
+}
+
+int mr_o_terrain_cull(const float* bbox, uint32_t n, uint32_t tile_rows, uint32_t tile_cols, const float xform[16],
+                      uint32_t* visible_out, uint32_t* visible_ids_out, uint32_t* idx_out, uint64_t counts_out[2]) {
+    uint32_t tiles_r, tiles_c, t, nvis = 0;
+    uint64_t nidx = 0;
+    if (!bbox || n < 2 || !tile_rows || !tile_cols) return MR_E_BADARG;
+    tiles_r = (n - 1u + tile_rows - 1u) / tile_rows;
+    tiles_c = (n - 1u + tile_cols - 1u) / tile_cols;
+    for (t = 0; t < tiles_r * tiles_c; ++t) {
+        int vis = mr_o_scene_node_should_render(xform, bbox + 8u * (size_t)t, bbox + 8u * (size_t)t + 4u);
+        if (visible_out) visible_out[t] = vis ? 1u : 0u;
+        if (vis) {
+            uint32_t tr = t / tiles_c, tc = t % tiles_c, r0 = tr * tile_rows, c0 = tc * tile_cols, r, c;
+            uint32_t qr = tile_rows < n - 1u - r0 ? tile_rows : n - 1u - r0;
+            uint32_t qc = tile_cols < n - 1u - c0 ? tile_cols : n - 1u - c0;
+            if (visible_ids_out) visible_ids_out[nvis] = t;
+            ++nvis;
+            for (r = r0; r < r0 + qr; ++r)
+                for (c = c0; c < c0 + qc; ++c) {
+                    if (idx_out) {
+                        uint32_t i00 = r * n + c;
+                        uint32_t* o = idx_out + nidx;
+                        o[0] = i00 + n; o[1] = i00; o[2] = i00 + n + 1u; o[3] = i00 + n + 1u; o[4] = i00; o[5] = i00 + 1u;
+                    }
+                    nidx += 6u;
+                }
+        }
+    }
+    if (counts_out) {
+        counts_out[0] = nvis;
+        counts_out[1] = nidx;
+    }
+    return MR_OK;
+}

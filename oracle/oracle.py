@@ -90,6 +90,14 @@ def lib() -> C.CDLL:
                                                  C.c_void_p]
         L.mr_o_test_lift_caps.restype = None
         L.mr_o_test_lift_caps.argtypes = [C.c_uint32]
+        L.mr_o_terrain_tile_bounds.restype = C.c_int
+        L.mr_o_terrain_tile_bounds.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.POINTER(MrTerrainParams), C.c_void_p]
+        L.mr_o_scene_node_should_render.restype = C.c_int
+        L.mr_o_scene_node_should_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mr_o_terrain_cull.restype = C.c_int
+        L.mr_o_terrain_cull.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.mr_o_time_create_polygon.restype = C.c_double
         L.mr_o_time_create_polygon.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.mr_o_hardware_threads.restype = C.c_int
@@ -228,6 +236,45 @@ def terrain_build(height, n, *, layout=TERRAINVERTEX, params=(0.2, 0.1, 5.0), ro
     if rc != 0:
         raise RuntimeError(f"oracle terrain_build rc={rc}")
     return vtx, idx
+
+
+def tile_count(n, tile_rows, tile_cols):
+    return (n - 1 + tile_rows - 1) // tile_rows, (n - 1 + tile_cols - 1) // tile_cols
+
+
+def terrain_tile_bounds(height, n, tile_rows, tile_cols, params=(0.2, 0.1, 5.0)) -> np.ndarray:
+    """[tiles, 8] f32: p0.xyzw, p1.xyzw per tile (tile t = tr * tiles_c + tc)."""
+    height = np.ascontiguousarray(height)
+    fmt = MR_HEIGHT_U16 if height.dtype == np.uint16 else MR_HEIGHT_F32
+    tr, tc = tile_count(n, tile_rows, tile_cols)
+    out = np.zeros((tr * tc, 8), dtype=np.float32)
+    p = MrTerrainParams(*params)
+    rc = lib().mr_o_terrain_tile_bounds(_ptr(height), fmt, n, tile_rows, tile_cols, C.byref(p), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle tile_bounds rc={rc}")
+    return out
+
+
+def scene_node_should_render(xform, p0, p1) -> bool:
+    """SceneNode.zig:96-110 for one bounding box; xform = 16 floats, memory image of mach.math.Mat4x4 (columns)."""
+    m = np.ascontiguousarray(xform, dtype=np.float32).reshape(16)
+    a = np.ascontiguousarray(p0, dtype=np.float32).reshape(4)
+    b = np.ascontiguousarray(p1, dtype=np.float32).reshape(4)
+    return bool(lib().mr_o_scene_node_should_render(_ptr(m), _ptr(a), _ptr(b)))
+
+
+def terrain_cull(bbox, n, tile_rows, tile_cols, xform, want_idx=True):
+    bbox = np.ascontiguousarray(bbox, dtype=np.float32)
+    m = np.ascontiguousarray(xform, dtype=np.float32).reshape(16)
+    ntiles = bbox.shape[0]
+    vis = np.zeros(ntiles, dtype=np.uint32)
+    ids = np.zeros(ntiles, dtype=np.uint32)
+    idx = np.zeros(6 * (n - 1) * (n - 1), dtype=np.uint32) if want_idx else None
+    counts = np.zeros(2, dtype=np.uint64)
+    rc = lib().mr_o_terrain_cull(_ptr(bbox), n, tile_rows, tile_cols, _ptr(m), _ptr(vis), _ptr(ids), _ptr(idx), _ptr(counts))
+    if rc != 0:
+        raise RuntimeError(f"oracle terrain_cull rc={rc}")
+    return dict(visible=vis, ids=ids[: int(counts[0])], idx=None if idx is None else idx[: int(counts[1])], counts=counts)
 
 
 def heightmap_normalize(u16: np.ndarray) -> np.ndarray:

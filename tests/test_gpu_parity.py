@@ -722,3 +722,48 @@ def test_terrain_host_band_into_larger_buffer(ctx, oracle):
     assert np.array_equal(vtx[a:z], ovtx[a:z]) and (vtx[:a] == 0x5A).all() and (vtx[z:] == 0x5A).all()
     a, z = 40 * 6 * (n - 1), 90 * 6 * (n - 1)
     assert np.array_equal(idx[a:z], oidx[a:z]) and (idx[:a] == 0x5A5A5A5A).all() and (idx[z:] == 0x5A5A5A5A).all()
+
+
+def test_terrain_tiles_and_cull_match_oracle(ctx, oracle):
+    """per-tile bounding boxes and the SceneNode.zig:96-110 visibility test on the GPU, with the
+    visible tiles compacted (ascending) into one index buffer -- bit-exact against the oracle, device and host pointers."""
+    from test_terrain_cull_cpu import camera_matrix, mat_image
+
+    torch = _torch()
+    lib = ctx.lib
+    for n, tr, tc in ((130, 32, 24), (1000, 64, 64), (257, 8, 256), (300, 500, 7)):
+        h = oracle.synth_heightmap_u16(0x5EED0001, n)
+        want_box = oracle.terrain_tile_bounds(h, n, tr, tc)
+        ntiles = want_box.shape[0]
+        hd = torch.from_numpy(h.view(np.int16)).cuda()
+        box_d = torch.empty(ntiles * 8, dtype=torch.float32, device="cuda")
+        ctx.check(lib.mr_terrain_tile_bounds(ctx.handle, hd.data_ptr(), 0, n, tr, tc, None, box_d.data_ptr()), "tile bounds")
+        ctx.sync()
+        assert np.array_equal(box_d.cpu().numpy().view(np.uint32), want_box.reshape(-1).view(np.uint32))
+        box_h = np.zeros((ntiles, 8), dtype=np.float32)  # host pointers, f32 heights
+        hf = oracle.heightmap_normalize(h)
+        ctx.check(lib.mr_terrain_tile_bounds(ctx.handle, hf.ctypes.data, 1, n, tr, tc, None, box_h.ctypes.data), "tile bounds")
+        assert np.array_equal(box_h.view(np.uint32), want_box.view(np.uint32))
+        mats = [camera_matrix(), camera_matrix((5.0, 60.0, 5.0), (40.0, 0.0, 40.0)), mat_image(np.array([[0, 0, 0, 1]] * 4, dtype=np.float32)),
+                mat_image(np.array([[0, 0, 0, -1], [0, 0, 0, 2], [0, 0, 0, 0], [0, 0, 0, 1]], dtype=np.float32))]
+        for m in mats:
+            ref = oracle.terrain_cull(want_box, n, tr, tc, m)
+            vis = torch.empty(ntiles, dtype=torch.int32, device="cuda")
+            ids = torch.empty(ntiles, dtype=torch.int32, device="cuda")
+            idx = torch.full((6 * (n - 1) * (n - 1),), -1, dtype=torch.int32, device="cuda")
+            cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+            ctx.check(lib.mr_terrain_cull(ctx.handle, box_d.data_ptr(), n, tr, tc, m.ctypes.data, vis.data_ptr(), ids.data_ptr(),
+                                          idx.data_ptr(), cnt.data_ptr()), "cull")
+            ctx.sync()
+            c = cnt.cpu().numpy()
+            assert c.tolist() == ref["counts"].tolist()
+            assert np.array_equal(vis.cpu().numpy().view(np.uint32), ref["visible"])
+            assert np.array_equal(ids.cpu().numpy().view(np.uint32)[: c[0]], ref["ids"])
+            g = idx.cpu().numpy().view(np.uint32)
+            assert np.array_equal(g[: c[1]], ref["idx"]) and (g[c[1]:] == 0xFFFFFFFF).all()
+            # host pointers, ids not requested
+            idx_h = np.zeros(6 * (n - 1) * (n - 1), dtype=np.uint32)
+            cnt_h = np.zeros(2, dtype=np.uint64)
+            ctx.check(lib.mr_terrain_cull(ctx.handle, want_box.ctypes.data, n, tr, tc, m.ctypes.data, None, None,
+                                          idx_h.ctypes.data, cnt_h.ctypes.data), "cull host")
+            assert cnt_h.tolist() == ref["counts"].tolist() and np.array_equal(idx_h[: int(cnt_h[1])], ref["idx"])
