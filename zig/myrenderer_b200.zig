@@ -64,6 +64,13 @@ pub extern fn mr_terrain_describe(n: u32, params: ?*const TerrainParams, bbox_mi
 pub extern fn mr_triangulate_batch(ctx: ?*Context, job: *const PolygonJob) c_int;
 pub extern fn mr_polygon_draw_range(first_tri_i: u64, first_tri_next: u64, tri_base: u64, out: *DrawRange) c_int;
 pub extern fn mr_unirand_seed_host(top: u32, seed: u64, index: u64, offset_out: *u32, prime_out: *u32) c_int;
+pub extern fn mr_context_trim(ctx: ?*Context) c_int;
+pub extern fn mr_pinned_alloc(ctx: ?*Context, bytes: usize, host_out: *?*anyopaque) c_int;
+pub extern fn mr_pinned_free(ctx: ?*Context, host: ?*anyopaque) c_int;
+// terrain tiles + culling (SceneNode.zig:96-110 per tile)
+pub extern fn mr_terrain_tile_count(n: u32, tile_rows: u32, tile_cols: u32, tiles_r_out: ?*u32, tiles_c_out: ?*u32) c_int;
+pub extern fn mr_terrain_tile_bounds(ctx: ?*Context, height: *const anyopaque, height_fmt: u32, n: u32, tile_rows: u32, tile_cols: u32, params: ?*const TerrainParams, bbox_out: [*]f32) c_int;
+pub extern fn mr_terrain_cull(ctx: ?*Context, bbox: [*]const f32, n: u32, tile_rows: u32, tile_cols: u32, xform: *const [16]f32, visible_out: ?[*]u32, visible_ids_out: ?[*]u32, idx_out: ?[*]u32, counts_out: ?*[2]u64) c_int;
 
 pub const Error = error{GeometryBackend};
 
