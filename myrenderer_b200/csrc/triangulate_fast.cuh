@@ -360,8 +360,103 @@ struct FPoly {
     __device__ bool pass2(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
         return gstack ? pass2_on<true>(p1, up, lo, lane, serial_below) : pass2_on<false>(p1, up, lo, lane, serial_below);
     }
+    // Pass 2 with one lane per stack entry (at most 32).  The loop :325-395 processes the crossed trapezoids in the
+    // order of their lower points (highest first) and ends with the one that holds the segment's lower point; every
+    // step converts its trapezoid into a segment node and closes the open trapezoid on the side its lower point lies
+    // on.  When the lower points above `lo` are pairwise distinct and exactly one entry has a lower point that is not
+    // above `lo` (the case of every consistent trapezoidation), the order is a sort, the node ids are a prefix count
+    // (left = A, right = A + 1, step s allocates A + 2 + s) and every write of the loop is a function of (own entry,
+    // the previous step that closed the same side): all steps can run at once.  Returns 1 done, 0 failed (status /
+    // requeue set as the loop would), -1 when the conditions do not hold (duplicates, null lower points, ...): the
+    // caller then runs the loop as written.
+    // MEASURED (round 2, B200): the single-entry case (the segment stays inside one trapezoid, about a third of the
+    // edges of a convex polygon) gains 1.3-2.4 % on the 8..1024-point batches; for 2..32 entries the lane-parallel
+    // form is bit-exact (the whole parity suite passes with MR_PASS2_PAR_MAX = 32) but 4-8 % SLOWER than the loop --
+    // with the 2-3 entries of sound input the ballots, MATCH and shuffle loops cost more than they save -- so it is
+    // compiled for one entry only.
+    __device__ __forceinline__ int pass2_parallel(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane) {
+        const uint32_t k = nstack;
+        const uint32_t A = nnodes;
+        const uint32_t cap = min(tier_node_cap, spec_node_cap);
+        const uint32_t seg_y = up | ((p1 == up) ? 0u : CRUMB_RIGHT) | (T_SEGMENT << 14) | (lo << 16);  // :351-360
+        if (k == 1u) {  // the segment stays inside one trapezoid: it becomes the segment node, both new trapezoids close
+            const uint32_t e = stack[0];
+            const uint2 w = nd[e];
+            const uint32_t np = w.y >> 16;
+            if (np == FNIL || np < lo) return -1;
+            if (A + 2u > cap) {
+                if (cap >= spec_node_cap) status |= MR_POLY_ARENA; else requeue = true;
+                return 0;
+            }
+            nnodes = A + 2u;
+            __syncwarp();
+            nd[e] = make_uint2(A | ((A + 1u) << 16), seg_y);
+            const uint32_t ty = up | (T_TRAPEZOID << 14) | (lo << 16);
+            nd[A] = make_uint2((w.x & 0xFFFFu) | (e << 16), ty);
+            nd[A + 1u] = make_uint2(e | (w.x & 0xFFFF0000u), ty);
+            return 1;
+        }
+        const bool act = lane < k;
+        const uint32_t e = act ? stack[lane] : 0u;
+        const uint2 w = nd[e];
+        const uint32_t np = w.y >> 16;
+        const bool in_s = act && np < lo;  // lower point strictly above `lo`: a step of its own
+        const uint32_t ms = __ballot_sync(0xFFFFFFFFu, in_s);
+        const uint32_t mr = __ballot_sync(0xFFFFFFFFu, act && !in_s);
+        const uint32_t same = __match_any_sync(0xFFFFFFFFu, in_s ? np : (0x10000u + lane));
+        const bool odd = (act && np == FNIL) || (same & (same - 1u)) != 0u;
+        if (__any_sync(0xFFFFFFFFu, odd) || __popc(mr) != 1) return -1;
+        const uint32_t m = __popc(ms);
+        if (A + 2u + m > cap) {  // the loop's failing add_node sees nnodes == cap
+            if (cap >= spec_node_cap) status |= MR_POLY_ARENA; else requeue = true;
+            return 0;
+        }
+        nnodes = A + 2u + m;
+        // step index: rank of the lower point among the steps; the entry holding `lo` comes last
+        uint32_t s = 0;
+        for (uint32_t j = 0; j < k; ++j) {
+            const uint32_t vj = __shfl_sync(0xFFFFFFFFu, np, j);
+            s += (((ms >> j) & 1u) && vj < np) ? 1u : 0u;
+        }
+        if (!in_s) s = m;
+        // :375 the side the step's lower point lies on
+        const bool is_left = in_s && left_of(sxy[np], up, lo);
+        const uint32_t ml = __ballot_sync(0xFFFFFFFFu, is_left);
+        // the previous step that closed (and re-opened) each side: largest step index below mine
+        uint32_t pl = 0, pr = 0;  // (step + 1) << 16 | lower point; 0 = none: the trapezoids allocated up front
+        for (uint32_t j = 0; j < k; ++j) {
+            const uint32_t sj = __shfl_sync(0xFFFFFFFFu, s, j);
+            const uint32_t vj = __shfl_sync(0xFFFFFFFFu, np, j);
+            if (((ms >> j) & 1u) && sj < s) {
+                const uint32_t key = ((sj + 1u) << 16) | vj;
+                if ((ml >> j) & 1u) pl = max(pl, key); else pr = max(pr, key);
+            }
+        }
+        const uint32_t left_id = pl ? A + 1u + (pl >> 16) : A;            // A + 2 + step
+        const uint32_t right_id = pr ? A + 1u + (pr >> 16) : A + 1u;
+        const uint32_t left_p1 = pl ? (pl & 0xFFFFu) : up;
+        const uint32_t right_p1 = pr ? (pr & 0xFFFFu) : up;
+        __syncwarp();
+        if (act) {
+            nd[e] = make_uint2(left_id | (right_id << 16), seg_y);                 // :347-360
+            const uint32_t low = in_s ? np : lo;
+            if (!in_s || is_left)                                                   // :366-369, :375-378
+                nd[left_id] = make_uint2((w.x & 0xFFFFu) | (e << 16), left_p1 | (T_TRAPEZOID << 14) | (low << 16));
+            if (!in_s || !is_left)                                                  // :370-372, :383-386
+                nd[right_id] = make_uint2(e | (w.x & 0xFFFF0000u), right_p1 | (T_TRAPEZOID << 14) | (low << 16));
+        }
+        return 1;
+    }
+
+#ifndef MR_PASS2_PAR_MAX
+#define MR_PASS2_PAR_MAX 1u  // see the measurement note above
+#endif
     template <bool GLOBAL>
     __device__ bool pass2_on(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
+        if (!GLOBAL && nstack <= MR_PASS2_PAR_MAX && nstack > 0u) {
+            const int r = pass2_parallel(p1, up, lo, lane);
+            if (r >= 0) return r != 0;
+        }
         uint16_t* const stk = GLOBAL ? gstack : stack;
         // The two open trapezoids live in registers until they are closed.
         uint32_t left = alloc();
