@@ -113,6 +113,8 @@ typedef struct mr_draw_range {
 typedef struct mr_context mr_context;
 
 int mr_abi_version(void);
+/* bit 0: bounds-checked build (-DMR_CHECKED, see myrenderer_b200/csrc/Makefile `checked`) */
+int mr_build_flags(void);
 int mr_device_count(int* count_out);
 int mr_context_create(int device, mr_context** ctx_out);
 int mr_context_destroy(mr_context* ctx);

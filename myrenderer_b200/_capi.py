@@ -102,7 +102,8 @@ class MrError(RuntimeError):
 
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libmyrenderer_b200.so")
+# MR_B200_LIB selects another build of the same library (the bounds-checked one: make -C myrenderer_b200/csrc checked)
+LIB_PATH = os.environ.get("MR_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libmyrenderer_b200.so")
 
 # name -> (restype, argtypes); also the list tests use to check that every declared symbol exports
 SIGNATURES = {
@@ -160,6 +161,7 @@ SIGNATURES = {
     "mr_terrain_cull": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                   C.c_void_p, C.c_void_p]),
+    "mr_build_flags": (C.c_int, []),
     "mr_context_trim": (C.c_int, [C.c_void_p]),
     "mr_context_scratch_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "mr_synth_polygons_family": (

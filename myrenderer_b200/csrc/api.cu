@@ -43,6 +43,14 @@ extern "C" {
 
 int mr_abi_version(void) { return MR_ABI_VERSION; }
 
+int mr_build_flags(void) {
+#ifdef MR_CHECKED
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 int mr_device_count(int* count_out) {
     if (!count_out) return MR_E_BADARG;
     int n = 0;

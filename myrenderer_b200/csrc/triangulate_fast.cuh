@@ -32,6 +32,42 @@
 //     O(k) scan of :329-337: same winner, because ties go to the lowest stack index in both.
 #pragma once
 
+// ---- checked build -----------------------------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this library was developed on, and the workspace below is full of
+// deliberate overlays (five arrays laid over dead space), which is where an out-of-bounds write hides.  Every workspace
+// array of the fast path is therefore declared through MR_SPAN / MR_MAKE_SPAN: in the product build these are raw
+// pointers (no cost); with -DMR_CHECKED (make -C myrenderer_b200/csrc checked) they carry their length and every
+// access traps on an index out of range.  tests/test_gpu_checked.py runs the parity cases against that library.
+#ifdef MR_CHECKED
+template <class T>
+struct mr_span {
+    T* p;
+    uint32_t n;
+    int line;
+    __device__ __forceinline__ T& operator[](size_t i) const {
+        if (i >= n) {
+            printf("MR_CHECKED: index %llu out of range %u (span declared at triangulate_fast.cuh:%d)\n", (unsigned long long)i, n, line);
+            __trap();
+        }
+        return p[i];
+    }
+    __device__ __forceinline__ bool is_null() const { return p == nullptr; }
+    template <class U>
+    __device__ __forceinline__ operator mr_span<U>() const { return mr_span<U>{p, n, line}; }  // T* -> const T*
+};
+#define MR_SPAN(T) mr_span<T>
+#define MR_MAKE_SPAN(T, ptr, len) (mr_span<T>{(ptr), (uint32_t)(len), __LINE__})
+#define MR_SPAN_NULL(T) (mr_span<T>{nullptr, 0u, __LINE__})
+#define MR_SPAN_IS_NULL(s) ((s).is_null())
+#define MR_SPAN_RAW(s) ((s).p)
+#else
+#define MR_SPAN(T) T*
+#define MR_MAKE_SPAN(T, ptr, len) (ptr)
+#define MR_SPAN_NULL(T) (static_cast<T*>(nullptr))
+#define MR_SPAN_IS_NULL(s) ((s) == nullptr)
+#define MR_SPAN_RAW(s) (s)
+#endif
+
 constexpr uint32_t FNIL14 = 0x1FFFu;  // null in the 13-bit pa field (ranks are < 1024 on this path)
 constexpr uint32_t CRUMB_RIGHT = 0x2000u;  // segment node: crumb == child2 (the inside is on the right)
 constexpr uint32_t FNIL = 0xFFFFu;
@@ -153,13 +189,13 @@ constexpr size_t PAR_GL_BYTES = ((size_t)PAR_GL_CAP * 3u * 2u + 127u) & ~(size_t
 enum : int { F_DONE = 0, F_REQUEUE_SPEC = 1, F_REQUEUE_GENERAL = 2 };
 
 struct FPoly {
-    const float2* sxy;
-    uint2* nd;
-    uint16_t* stack;   // node_stack of the segment being inserted: always shared memory ...
-    uint16_t* gstack;  // ... unless this is non-null: the (rare) list that only fitted the global-memory scratch.
+    MR_SPAN(const float2) sxy;
+    MR_SPAN(uint2) nd;
+    MR_SPAN(uint16_t) stack;   // node_stack of the segment being inserted: always shared memory ...
+    MR_SPAN(uint16_t) gstack;  // ... unless this is non-null: the (rare) list that only fitted the global-memory scratch.
                        // Two members so that the compiler keeps `stack` in the shared address space (LDS/STS, no
                        // generic-pointer arithmetic on the hot path).
-    uint16_t* cstack;
+    MR_SPAN(uint16_t) cstack;
     uint32_t nnodes, nstack, status;
     uint32_t tier_node_cap, tier_stack_cap, spec_node_cap, spec_stack_cap;
     bool requeue;
@@ -291,8 +327,8 @@ struct FPoly {
     //   it_node/it_next: item arrays (cap entries), out: node_stack to fill (out_cap entries), ctr: shared
     //   word.  Returns 1 done, 0 failure (status/requeue set).
     template <bool GLOBAL>
-    __device__ int search_parallel(uint32_t up, uint32_t lo, uint16_t* it_node, uint16_t* it_next, uint32_t cap,
-                                   uint16_t* out, uint32_t out_cap, uint32_t* ctr, uint32_t lane) {
+    __device__ int search_parallel(uint32_t up, uint32_t lo, MR_SPAN(uint16_t) it_node, MR_SPAN(uint16_t) it_next, uint32_t cap,
+                                   MR_SPAN(uint16_t) out, uint32_t out_cap, MR_SPAN(uint32_t) ctr, uint32_t lane) {
         const float2 Pu = sxy[up], Pl = sxy[lo];
         __syncwarp();
         if (lane == 0) {
@@ -358,7 +394,7 @@ struct FPoly {
 
     // pass 2 of add_segment (:316-395) on node_stack; p1 is the rank id of the edge's first point
     __device__ bool pass2(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
-        return gstack ? pass2_on<true>(p1, up, lo, lane, serial_below) : pass2_on<false>(p1, up, lo, lane, serial_below);
+        return !MR_SPAN_IS_NULL(gstack) ? pass2_on<true>(p1, up, lo, lane, serial_below) : pass2_on<false>(p1, up, lo, lane, serial_below);
     }
     // Pass 2 with one lane per stack entry (at most 32).  The loop :325-395 processes the crossed trapezoids in the
     // order of their lower points (highest first) and ends with the one that holds the segment's lower point; every
@@ -457,7 +493,7 @@ struct FPoly {
             const int r = pass2_parallel(p1, up, lo, lane);
             if (r >= 0) return r != 0;
         }
-        uint16_t* const stk = GLOBAL ? gstack : stack;
+        MR_SPAN(uint16_t) stk = GLOBAL ? gstack : stack;
         // The two open trapezoids live in registers until they are closed.
         uint32_t left = alloc();
         if (left == FNIL) return false;
@@ -577,9 +613,12 @@ __device__ __forceinline__ void team_sync() {
 }
 
 struct FItems {
-    uint16_t *it_node, *it_next, *it_edge, *ehead;
-    const uint16_t* rk;  // rank of original point i: edge e runs from rk[e] to rk[e+1 mod n]
-    uint32_t* ctr;
+    MR_SPAN(uint16_t) it_node;
+    MR_SPAN(uint16_t) it_next;
+    MR_SPAN(uint16_t) it_edge;
+    MR_SPAN(uint16_t) ehead;
+    MR_SPAN(const uint16_t) rk;  // rank of original point i: edge e runs from rk[e] to rk[e+1 mod n]
+    MR_SPAN(uint32_t) ctr;
     uint32_t cap;
 };
 
@@ -617,7 +656,7 @@ __device__ __forceinline__ void advance_item(const FPoly& P, const FItems& I, ui
 // Lane-parallel advance of every pending point's cached location and (do_items) of every pending edge's search.
 // Called by all W*32 threads of the team with the same arguments; tid = 0 .. W*32-1.
 template <int W>
-__device__ __forceinline__ void team_refresh(const float2* sxy, uint2* nd, uint16_t* loc, uint32_t n, bool do_items,
+__device__ __forceinline__ void team_refresh(MR_SPAN(const float2) sxy, MR_SPAN(uint2) nd, MR_SPAN(uint16_t) loc, uint32_t n, bool do_items,
                                              const FItems I, uint32_t items_end, uint32_t tid) {
     constexpr uint32_t T = (uint32_t)W * 32u;
     FPoly P;  // only the immutable views are used here (locate, dfs_step)
@@ -645,15 +684,15 @@ __device__ __forceinline__ void team_refresh(const float2* sxy, uint2* nd, uint1
 // Load, validate and rank a polygon's points; all W*32 threads of the team call it (tid = 0 .. W*32-1).
 // Returns 0 ok, 1 non-finite coordinate, 2 coincident points (same value on every thread).
 template <int W>
-__device__ __forceinline__ int team_load_rank(const float2* src, unsigned char* ws, const FLayout& L, uint32_t n, uint32_t tid,
-                                              TeamShared* ts) {
+__device__ __forceinline__ int team_load_rank(const float2* src, unsigned char* ws, const FCaps& caps, const FLayout& L, uint32_t n,
+                                              uint32_t tid, TeamShared* ts) {
     constexpr uint32_t T = (uint32_t)W * 32u;
-    float2* sxy = reinterpret_cast<float2*>(ws + L.sxy);
-    uint16_t* orig = reinterpret_cast<uint16_t*>(ws + L.orig);
-    uint16_t* rk = reinterpret_cast<uint16_t*>(ws + L.rk);
-    uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
+    MR_SPAN(float2) sxy = MR_MAKE_SPAN(float2, reinterpret_cast<float2*>(ws + L.sxy), caps.nmax);
+    MR_SPAN(uint16_t) orig = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.orig), caps.nmax);
+    MR_SPAN(uint16_t) rk = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.rk), caps.nmax);
+    MR_SPAN(uint16_t) loc = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.loc), caps.nmax);
     // Original coordinates are staged in the node arena (free until the trapezoidation starts).
-    float2* raw = reinterpret_cast<float2*>(ws + L.nodes);
+    MR_SPAN(float2) raw = MR_MAKE_SPAN(float2, reinterpret_cast<float2*>(ws + L.nodes), n);
     bool finite = true;
     for (uint32_t i = tid; i < n; i += T) {
         const float2 v = __ldg(src + i);
@@ -674,8 +713,10 @@ __device__ __forceinline__ int team_load_rank(const float2* src, unsigned char* 
     // as floats, so the key maps both to +0; the emitted coordinates still come from `raw`.
     uint32_t n2 = 32;
     while (n2 < n) n2 <<= 1;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + L.nodes) + n;  // 8n + 8*n2 <= 8*node_cap
-    uint16_t* kidx = reinterpret_cast<uint16_t*>(ws + L.add_pp);                        // 2*n2 <= 4n <= 4*add_cap
+    // 8n + 8*n2 <= 8*node_cap and 2*n2 <= 4n <= 4*add_cap (fast_layout_ok)
+    MR_SPAN(unsigned long long) keys = MR_MAKE_SPAN(unsigned long long, reinterpret_cast<unsigned long long*>(ws + L.nodes) + n,
+                                                    min(n2, caps.node_cap - n));
+    MR_SPAN(uint16_t) kidx = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.add_pp), min(n2, 2u * caps.add_cap));
     for (uint32_t i = tid; i < n2; i += T) {
         unsigned long long k = ~0ull;  // padding sorts last
         if (i < n) {
@@ -752,22 +793,23 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
     constexpr uint32_t TT = (uint32_t)W * 32u;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const float2* sxy = reinterpret_cast<const float2*>(ws + L.sxy);
-    const uint16_t* orig = reinterpret_cast<const uint16_t*>(ws + L.orig);
-    const uint32_t* add_pp = reinterpret_cast<const uint32_t*>(ws + L.add_pp);
-    const uint16_t* add_m = reinterpret_cast<const uint16_t*>(ws + L.add_m);
-    uint32_t* mcount = reinterpret_cast<uint32_t*>(ws + L.mcount);
-    const uint16_t* mstart = reinterpret_cast<const uint16_t*>(ws + L.mstart);
+    MR_SPAN(const float2) sxy = MR_MAKE_SPAN(const float2, reinterpret_cast<const float2*>(ws + L.sxy), caps.nmax);
+    MR_SPAN(const uint16_t) orig = MR_MAKE_SPAN(const uint16_t, reinterpret_cast<const uint16_t*>(ws + L.orig), caps.nmax);
+    MR_SPAN(const uint32_t) add_pp = MR_MAKE_SPAN(const uint32_t, reinterpret_cast<const uint32_t*>(ws + L.add_pp), caps.add_cap);
+    MR_SPAN(const uint16_t) add_m = MR_MAKE_SPAN(const uint16_t, reinterpret_cast<const uint16_t*>(ws + L.add_m), caps.add_cap);
+    MR_SPAN(uint32_t) mcount = MR_MAKE_SPAN(uint32_t, reinterpret_cast<uint32_t*>(ws + L.mcount), caps.add_cap);
+    MR_SPAN(const uint16_t) mstart = MR_MAKE_SPAN(const uint16_t, reinterpret_cast<const uint16_t*>(ws + L.mstart), caps.add_cap + 1u);
 
     // ---- group entries by mountain, stable sort by (rank, append position)  (:555) ----------------
     // sort arrays alias the node arena: Gpos, cum, Gid, Gm, S -- u16 each, E = 2A entries
     const uint32_t E = 2u * A;
     const size_t ecap = (size_t)caps.add_cap * 2;
-    uint16_t* Gpos = reinterpret_cast<uint16_t*>(ws + L.nodes);
-    uint16_t* cum = Gpos + ecap;
-    uint16_t* Gid = cum + ecap;
-    uint16_t* Gm = Gid + ecap;
-    uint16_t* S = Gm + ecap;
+    uint16_t* const sort0 = reinterpret_cast<uint16_t*>(ws + L.nodes);
+    MR_SPAN(uint16_t) Gpos = MR_MAKE_SPAN(uint16_t, sort0, ecap);
+    MR_SPAN(uint16_t) cum = MR_MAKE_SPAN(uint16_t, sort0 + ecap, ecap);
+    MR_SPAN(uint16_t) Gid = MR_MAKE_SPAN(uint16_t, sort0 + 2 * ecap, ecap);
+    MR_SPAN(uint16_t) Gm = MR_MAKE_SPAN(uint16_t, sort0 + 3 * ecap, ecap);
+    MR_SPAN(uint16_t) S = MR_MAKE_SPAN(uint16_t, sort0 + 4 * ecap, ecap);
     for (uint32_t ai = tid; ai < A; ai += TT) {
         const uint32_t m = add_m[ai];
         const uint32_t pp = add_pp[ai];
@@ -803,7 +845,7 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
                 if (g >= s + 2u) {
                     const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
                     valid = (c != a1) && (c != a2);
-                    if (valid && !is_acute_shortcut(sxy, c, a1, a2)) all_acute = false;
+                    if (valid && !is_acute_shortcut(MR_SPAN_RAW(sxy), c, a1, a2)) all_acute = false;
                 }
             }
             const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
@@ -824,7 +866,7 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
             if (g >= s + 2u) {
                 const uint32_t c = S[g], a1 = S[g - 1], a2 = S[s];
                 valid = (c != a1) && (c != a2);
-                if (valid && !is_acute_shortcut(sxy, c, a1, a2)) all_acute = false;
+                if (valid && !is_acute_shortcut(MR_SPAN_RAW(sxy), c, a1, a2)) all_acute = false;
             }
             cum[g] = valid ? 1u : 0u;
         }
@@ -848,7 +890,7 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
 
     float mn = 0.0f, mx = 0.0f, lasty = 0.0f;
     bool has_last = false;
-    uint16_t* tri = Gpos;  // Gpos is dead after the sort; 2*add_cap entries >= 3*cap_tri
+    MR_SPAN(uint16_t) tri = Gpos;  // Gpos is dead after the sort; 2*add_cap entries >= 3*cap_tri
     for (uint32_t g = tid; g < E; g += TT) {
         const uint32_t m = Gm[g];
         const uint32_t s = mstart[m], t = mstart[m + 1];
@@ -933,12 +975,12 @@ __device__ __forceinline__ int team_finish(const Sink& sink, uint32_t cap_tri, u
 
 __device__ __forceinline__ FItems fast_items(unsigned char* ws, const FLayout& L, const FCaps& caps) {
     FItems I;
-    I.it_node = reinterpret_cast<uint16_t*>(ws + L.it_node);
-    I.it_next = reinterpret_cast<uint16_t*>(ws + L.it_next);
-    I.it_edge = reinterpret_cast<uint16_t*>(ws + L.it_edge);
-    I.ehead = reinterpret_cast<uint16_t*>(ws + L.ehead);
-    I.rk = reinterpret_cast<const uint16_t*>(ws + L.rk);
-    I.ctr = reinterpret_cast<uint32_t*>(ws + L.ctr);  // [0] items allocated, [1] pool overflow flag
+    I.it_node = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.it_node), caps.item_cap);
+    I.it_next = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.it_next), caps.item_cap);
+    I.it_edge = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.it_edge), caps.item_cap);
+    I.ehead = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.ehead), caps.item_cap ? caps.nmax : 0u);
+    I.rk = MR_MAKE_SPAN(const uint16_t, reinterpret_cast<const uint16_t*>(ws + L.rk), caps.nmax);
+    I.ctr = MR_MAKE_SPAN(uint32_t, reinterpret_cast<uint32_t*>(ws + L.ctr), caps.item_cap ? 4u : 0u);  // [0] items allocated, [1] pool overflow flag
     I.cap = caps.item_cap;
     return I;
 }
@@ -948,9 +990,9 @@ template <int W>
 __device__ void team_helper(const BatchArgs& a, uint32_t pi, unsigned char* ws, const FCaps caps, const FLayout L,
                             TeamShared* ts) {
     FPoly P;
-    P.sxy = reinterpret_cast<const float2*>(ws + L.sxy);
-    P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
-    uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
+    P.sxy = MR_MAKE_SPAN(const float2, reinterpret_cast<const float2*>(ws + L.sxy), caps.nmax);
+    P.nd = MR_MAKE_SPAN(uint2, reinterpret_cast<uint2*>(ws + L.nodes), caps.node_cap);
+    MR_SPAN(uint16_t) loc = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.loc), caps.nmax);
     const FItems I = fast_items(ws, L, caps);
     for (;;) {
         team_bar<W>();
@@ -961,7 +1003,7 @@ __device__ void team_helper(const BatchArgs& a, uint32_t pi, unsigned char* ws, 
             team_bar<W>();
         } else if (cmd == TEAM_LOAD) {
             const uint64_t p0 = a.first_point[pi] - a.point_base;
-            team_load_rank<W>(reinterpret_cast<const float2*>(a.xy) + p0, ws, L, ts->n, threadIdx.x, ts);
+            team_load_rank<W>(reinterpret_cast<const float2*>(a.xy) + p0, ws, caps, L, ts->n, threadIdx.x, ts);
         } else {  // TEAM_FINISH
             uint32_t cap_tri;
             const Sink sink = fast_sink(a, pi, &cap_tri);
@@ -1001,10 +1043,10 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     }
     if (n > caps.nmax) return F_REQUEUE_GENERAL;
 
-    float2* sxy = reinterpret_cast<float2*>(ws + L.sxy);
-    uint16_t* orig = reinterpret_cast<uint16_t*>(ws + L.orig);
-    uint16_t* rk = reinterpret_cast<uint16_t*>(ws + L.rk);
-    uint16_t* loc = reinterpret_cast<uint16_t*>(ws + L.loc);
+    MR_SPAN(float2) sxy = MR_MAKE_SPAN(float2, reinterpret_cast<float2*>(ws + L.sxy), caps.nmax);
+    MR_SPAN(uint16_t) orig = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.orig), caps.nmax);
+    MR_SPAN(uint16_t) rk = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.rk), caps.nmax);
+    MR_SPAN(uint16_t) loc = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.loc), caps.nmax);
 
     // ---- load, validate, rank (all warps of the team) ------------------------------------------------
     if (W > 1) {
@@ -1016,7 +1058,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         team_bar<W>();
     }
     {
-        const int lr = team_load_rank<W>(reinterpret_cast<const float2*>(a.xy) + p0, ws, L, n, lane, ts);
+        const int lr = team_load_rank<W>(reinterpret_cast<const float2*>(a.xy) + p0, ws, caps, L, n, lane, ts);
         if (lr == 1) {
             res->status = MR_POLY_NONFINITE;
             sink.zero(0, sink.cap_vtx, lane);
@@ -1037,10 +1079,10 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     // ---- part 1: trapezoidation ---------------------------------------------------------------------
     FPoly P;
     P.sxy = sxy;
-    P.nd = reinterpret_cast<uint2*>(ws + L.nodes);
-    P.stack = reinterpret_cast<uint16_t*>(ws + L.stack);
-    P.cstack = reinterpret_cast<uint16_t*>(ws + L.cstack);
-    P.gstack = nullptr;
+    P.nd = MR_MAKE_SPAN(uint2, reinterpret_cast<uint2*>(ws + L.nodes), caps.node_cap);
+    P.stack = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.stack), caps.stack_cap);
+    P.cstack = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.cstack), caps.item_cap ? 0u : caps.nmax);
+    P.gstack = MR_SPAN_NULL(uint16_t);
     P.nnodes = 1;  // :479 root trapezoid
     P.nstack = 0;
     P.status = MR_POLY_OK;
@@ -1067,8 +1109,11 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     const uint32_t item_mult = W > 1 ? MR_TEAM_ITEM_MULT : 4u;
     uint32_t refresh_wait = 0, item_wait = 0;
     const FItems I = fast_items(ws, L, caps);
-    uint16_t *const it_node = I.it_node, *const it_next = I.it_next, *const it_edge = I.it_edge, *const ehead = I.ehead;
-    uint32_t* const ctr = I.ctr;
+    MR_SPAN(uint16_t) it_node = I.it_node;
+    MR_SPAN(uint16_t) it_next = I.it_next;
+    MR_SPAN(uint16_t) it_edge = I.it_edge;
+    MR_SPAN(uint16_t) ehead = I.ehead;
+    MR_SPAN(uint32_t) ctr = I.ctr;
     if (use_items) {
         for (uint32_t e = lane; e < n; e += 32) {  // every edge starts with one item at the root
             it_node[e] = 0;
@@ -1084,13 +1129,15 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     __syncwarp();
 
     // scratch of the parallel search (tiers without conflict lists): the mountain-phase arrays, free in part 1
-    uint16_t* const stack_home = P.stack;
-    uint16_t *par_node = nullptr, *par_next = nullptr, *par_out = nullptr;
-    uint32_t* par_ctr = nullptr;
+    MR_SPAN(uint16_t) stack_home = P.stack;
+    MR_SPAN(uint16_t) par_node = MR_SPAN_NULL(uint16_t);
+    MR_SPAN(uint16_t) par_next = MR_SPAN_NULL(uint16_t);
+    MR_SPAN(uint16_t) par_out = MR_SPAN_NULL(uint16_t);
+    MR_SPAN(uint32_t) par_ctr = MR_SPAN_NULL(uint32_t);
     uint32_t par_cap = 0, par_out_cap = 0;
     if (!use_items) {
         const size_t bytes = (L.efirst == L.loc ? L.total : L.efirst) - L.add_pp - 16;  // pool region minus the counter
-        par_ctr = reinterpret_cast<uint32_t*>(ws + L.add_pp);
+        par_ctr = MR_MAKE_SPAN(uint32_t, reinterpret_cast<uint32_t*>(ws + L.add_pp), 4u);
         unsigned char* base = ws + L.add_pp + 16;
         if (caps.par_separate_out) {  // retry tier: the list goes to the (contract-cap) node_stack itself
             par_cap = (uint32_t)(bytes / 4);
@@ -1098,11 +1145,11 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             par_out_cap = caps.stack_cap;
         } else {  // typical-case tier: items and the output list share the region 2:1
             par_cap = (uint32_t)(bytes / 6);
-            par_out = reinterpret_cast<uint16_t*>(base + (size_t)par_cap * 4);
+            par_out = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(base + (size_t)par_cap * 4), par_cap);
             par_out_cap = par_cap;
         }
-        par_node = reinterpret_cast<uint16_t*>(base);
-        par_next = par_node + par_cap;
+        par_node = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(base), par_cap);
+        par_next = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(base) + par_cap, par_cap);
     }
 
     const bool ur_simple = ur_offset < n && ur_prime < n;
@@ -1258,7 +1305,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
             // redone as a parallel frontier expansion (items + output list live in the mountain arrays,
             // unused during part 1)
             P.stack = stack_home;
-            P.gstack = nullptr;
+            P.gstack = MR_SPAN_NULL(uint16_t);
             const int sr = P.search_from_root(up, lo, par_cap ? 48u : 0xFFFFFFFFu);
             if (sr == 2) {
                 if (!P.search_parallel<false>(up, lo, par_node, par_next, par_cap, par_out, par_out_cap, par_ctr, lane)) {
@@ -1269,7 +1316,8 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
                         // -- cheaper than sending the polygon to the retry launch, whose few polygons run alone on the GPU.
                         P.requeue = false;
                         uint16_t* g = reinterpret_cast<uint16_t*>(par_gl);
-                        ok = P.search_parallel<true>(up, lo, g, g + PAR_GL_CAP, PAR_GL_CAP, g + 2u * PAR_GL_CAP, PAR_GL_CAP, par_ctr, lane) != 0;
+                        ok = P.search_parallel<true>(up, lo, MR_MAKE_SPAN(uint16_t, g, PAR_GL_CAP), MR_MAKE_SPAN(uint16_t, g + PAR_GL_CAP, PAR_GL_CAP),
+                                                     PAR_GL_CAP, MR_MAKE_SPAN(uint16_t, g + 2u * PAR_GL_CAP, PAR_GL_CAP), PAR_GL_CAP, par_ctr, lane) != 0;
                     }
                 }
             } else if (sr == 0) {
@@ -1298,12 +1346,12 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     }
 
     // ---- part 2: inside trapezoids -> adds, in node id order (:510-540) ---------------------------
-    uint32_t* add_pp = reinterpret_cast<uint32_t*>(ws + L.add_pp);
-    uint32_t* add_key = reinterpret_cast<uint32_t*>(ws + L.add_key);
-    uint16_t* add_m = reinterpret_cast<uint16_t*>(ws + L.add_m);
-    uint32_t* mcount = reinterpret_cast<uint32_t*>(ws + L.mcount);
-    uint16_t* mstart = reinterpret_cast<uint16_t*>(ws + L.mstart);
-    uint16_t* efirst = reinterpret_cast<uint16_t*>(ws + L.efirst);
+    MR_SPAN(uint32_t) add_pp = MR_MAKE_SPAN(uint32_t, reinterpret_cast<uint32_t*>(ws + L.add_pp), caps.add_cap);
+    MR_SPAN(uint32_t) add_key = MR_MAKE_SPAN(uint32_t, reinterpret_cast<uint32_t*>(ws + L.add_key), caps.add_cap);
+    MR_SPAN(uint16_t) add_m = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.add_m), caps.add_cap);
+    MR_SPAN(uint32_t) mcount = MR_MAKE_SPAN(uint32_t, reinterpret_cast<uint32_t*>(ws + L.mcount), caps.add_cap);
+    MR_SPAN(uint16_t) mstart = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.mstart), caps.add_cap + 1u);
+    MR_SPAN(uint16_t) efirst = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.efirst), caps.nmax);
     const uint32_t PMASK = 0xFFFF1FFFu;  // (pa, pb) without the type and crumb bits
 
     uint32_t A = 0;
