@@ -238,9 +238,18 @@ struct FPoly {
     // :169-192 split trapezoid `base` at point pid
     __device__ __forceinline__ bool split(uint32_t base, uint32_t pid) {
         const uint2 v = nd[base];
-        const uint32_t lower = alloc();  // :178 lower first
-        const uint32_t upper = alloc();  // :179
-        if (lower == FNIL || upper == FNIL) return false;
+        if (nnodes + 2u > min(tier_node_cap, spec_node_cap)) {  // both clones at once (the failing alloc decides the flag)
+            if (nnodes + 1u > min(tier_node_cap, spec_node_cap)) {
+                alloc();
+            } else {
+                alloc();
+                alloc();
+            }
+            return false;
+        }
+        const uint32_t lower = nnodes;      // :178 lower first
+        const uint32_t upper = nnodes + 1u;  // :179
+        nnodes += 2u;
         nd[lower] = make_uint2(v.x, (v.y & 0xFFFFC000u) | pid);        // point1 = pid
         nd[upper] = make_uint2(v.x, (v.y & 0x0000FFFFu) | (pid << 16));  // point2 = pid
         nd[base] = make_uint2(upper | (lower << 16), pid | (T_POINT << 14) | (FNIL << 16));
@@ -432,6 +441,39 @@ struct FPoly {
             nd[A + 1u] = make_uint2(e | (w.x & 0xFFFF0000u), ty);
             return 1;
         }
+#ifndef MR_PASS2_NO_K2
+        if (k == 2u) {  // one trapezoid above the one that holds `lo`: one step plus the final one, written out straight
+            const uint32_t e0 = stack[0], e1 = stack[1];
+            const uint2 w0 = nd[e0], w1 = nd[e1];
+            const uint32_t n0 = w0.y >> 16, n1 = w1.y >> 16;
+            if (n0 == FNIL || n1 == FNIL || ((n0 < lo) == (n1 < lo))) return -1;
+            if (A + 3u > cap) {
+                if (cap >= spec_node_cap) status |= MR_POLY_ARENA; else requeue = true;
+                return 0;
+            }
+            nnodes = A + 3u;
+            const bool first0 = n0 < lo;  // which entry is the step
+            const uint32_t es = first0 ? e0 : e1, ef = first0 ? e1 : e0;
+            const uint32_t xs = first0 ? w0.x : w1.x, xf = first0 ? w1.x : w0.x;
+            const uint32_t nps = first0 ? n0 : n1;
+            const bool is_left = left_of(sxy[nps], up, lo);  // :375
+            const uint32_t t_up = up | (T_TRAPEZOID << 14), t_mid = nps | (T_TRAPEZOID << 14);
+            __syncwarp();
+            nd[es] = make_uint2(A | ((A + 1u) << 16), seg_y);
+            if (is_left) {  // the left trapezoid closes at the step; a new one (A + 2) runs down to `lo`
+                nd[A] = make_uint2((xs & 0xFFFFu) | (es << 16), t_up | (nps << 16));
+                nd[A + 2u] = make_uint2((xf & 0xFFFFu) | (ef << 16), t_mid | (lo << 16));
+                nd[A + 1u] = make_uint2(ef | (xf & 0xFFFF0000u), t_up | (lo << 16));
+                nd[ef] = make_uint2((A + 2u) | ((A + 1u) << 16), seg_y);
+            } else {
+                nd[A + 1u] = make_uint2(es | (xs & 0xFFFF0000u), t_up | (nps << 16));
+                nd[A + 2u] = make_uint2(ef | (xf & 0xFFFF0000u), t_mid | (lo << 16));
+                nd[A] = make_uint2((xf & 0xFFFFu) | (ef << 16), t_up | (lo << 16));
+                nd[ef] = make_uint2(A | ((A + 2u) << 16), seg_y);
+            }
+            return 1;
+        }
+#endif
         const bool act = lane < k;
         const uint32_t e = act ? stack[lane] : 0u;
         const uint2 w = nd[e];
@@ -485,7 +527,7 @@ struct FPoly {
     }
 
 #ifndef MR_PASS2_PAR_MAX
-#define MR_PASS2_PAR_MAX 1u  // see the measurement note above
+#define MR_PASS2_PAR_MAX 2u  // see the measurement note above (1 and 2 entries: the straight-line forms)
 #endif
     template <bool GLOBAL>
     __device__ bool pass2_on(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
