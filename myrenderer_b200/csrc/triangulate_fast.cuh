@@ -405,6 +405,92 @@ struct FPoly {
     __device__ bool pass2(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
         return !MR_SPAN_IS_NULL(gstack) ? pass2_on<true>(p1, up, lo, lane, serial_below) : pass2_on<false>(p1, up, lo, lane, serial_below);
     }
+    // Pass 2 for a stack of K <= 4 entries, written out straight (every lane runs the same code; no loop, no
+    // selection scan).  The loop :325-395 takes the crossed trapezoids in the order of their lower points (highest
+    // first) and ends with the one that holds the segment's lower point; each step converts its trapezoid into a
+    // segment node and closes the open trapezoid on the side its lower point lies on (:375), opening a new one there.
+    // With all lower points non-null, those above `lo` pairwise distinct and exactly one entry whose lower point is not
+    // above `lo` -- the case of every consistent trapezoidation -- that order is a sort by lower point, and the node
+    // ids are known up front (left = A, right = A + 1, step s allocates A + 2 + s).  All loads are issued together and
+    // the side tests are independent, which is what the latency-bound main warp of a polygon needs.  Returns 1 done,
+    // 0 failed (status / requeue set as the loop would), -1 when the conditions do not hold: the caller then runs the
+    // loop as written.
+    template <int K>
+    __device__ __forceinline__ int pass2_small(uint32_t p1, uint32_t up, uint32_t lo) {
+        const uint32_t A = nnodes;
+        const uint32_t cap = min(tier_node_cap, spec_node_cap);
+        uint32_t e[K], x[K], np[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) e[i] = stack[i];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const uint2 w = nd[e[i]];
+            x[i] = w.x;
+            np[i] = w.y >> 16;
+        }
+        bool odd = false;
+        int finals = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            odd = odd || np[i] == FNIL;
+            finals += np[i] < lo ? 0 : 1;
+#pragma unroll
+            for (int j = i + 1; j < K; ++j) odd = odd || (np[i] == np[j]);  // (a duplicate of the last entry shows up in `finals`)
+        }
+        if (odd || finals != 1) return -1;
+        if (A + (uint32_t)K + 1u > cap) {  // the loop's failing add_node sees nnodes == cap
+            if (cap >= spec_node_cap) status |= MR_POLY_ARENA; else requeue = true;
+            return 0;
+        }
+        nnodes = A + (uint32_t)K + 1u;
+        // ascending lower point: the steps in the loop's order, then the entry that holds `lo`
+#define MR_CSWAP(a, b)                                  \
+    {                                                   \
+        const bool sw_ = np[a] > np[b];                 \
+        const uint32_t n_ = sw_ ? np[b] : np[a];        \
+        const uint32_t e_ = sw_ ? e[b] : e[a];          \
+        const uint32_t x_ = sw_ ? x[b] : x[a];          \
+        np[b] = sw_ ? np[a] : np[b];                    \
+        e[b] = sw_ ? e[a] : e[b];                       \
+        x[b] = sw_ ? x[a] : x[b];                       \
+        np[a] = n_;                                     \
+        e[a] = e_;                                      \
+        x[a] = x_;                                      \
+    }
+        if (K == 2) {
+            MR_CSWAP(0, 1)
+        } else if (K == 3) {
+            MR_CSWAP(0, 1) MR_CSWAP(1, 2) MR_CSWAP(0, 1)
+        } else if (K == 4) {
+            MR_CSWAP(0, 1) MR_CSWAP(2, 3) MR_CSWAP(0, 2) MR_CSWAP(1, 3) MR_CSWAP(1, 2)
+        }
+#undef MR_CSWAP
+        bool is_left[K];  // :375, one independent test per step
+#pragma unroll
+        for (int i = 0; i + 1 < K; ++i) is_left[i] = left_of(sxy[np[i]], up, lo);
+        const uint32_t seg_y = up | ((p1 == up) ? 0u : CRUMB_RIGHT) | (T_SEGMENT << 14) | (lo << 16);  // :351-360
+        const uint32_t trap = T_TRAPEZOID << 14;
+        uint32_t cur_l = A, cur_r = A + 1u, p_l = up, p_r = up;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i + 1 < K; ++i) {
+            nd[e[i]] = make_uint2(cur_l | (cur_r << 16), seg_y);  // :347-360
+            if (is_left[i]) {                                       // :375-382
+                nd[cur_l] = make_uint2((x[i] & 0xFFFFu) | (e[i] << 16), p_l | trap | (np[i] << 16));
+                cur_l = A + 2u + (uint32_t)i;
+                p_l = np[i];
+            } else {                                                // :383-391
+                nd[cur_r] = make_uint2(e[i] | (x[i] & 0xFFFF0000u), p_r | trap | (np[i] << 16));
+                cur_r = A + 2u + (uint32_t)i;
+                p_r = np[i];
+            }
+        }
+        nd[e[K - 1]] = make_uint2(cur_l | (cur_r << 16), seg_y);     // :366-373
+        nd[cur_l] = make_uint2((x[K - 1] & 0xFFFFu) | (e[K - 1] << 16), p_l | trap | (lo << 16));
+        nd[cur_r] = make_uint2(e[K - 1] | (x[K - 1] & 0xFFFF0000u), p_r | trap | (lo << 16));
+        return 1;
+    }
+
     // Pass 2 with one lane per stack entry (at most 32).  The loop :325-395 processes the crossed trapezoids in the
     // order of their lower points (highest first) and ends with the one that holds the segment's lower point; every
     // step converts its trapezoid into a segment node and closes the open trapezoid on the side its lower point lies
@@ -526,12 +612,24 @@ struct FPoly {
         return 1;
     }
 
+#ifndef MR_PASS2_SMALL_MAX
+#define MR_PASS2_SMALL_MAX 2u  // straight-line pass 2 for stacks of up to this many entries (<= 4; measured: 2 best overall)
+#endif
 #ifndef MR_PASS2_PAR_MAX
-#define MR_PASS2_PAR_MAX 2u  // see the measurement note above (1 and 2 entries: the straight-line forms)
+#define MR_PASS2_PAR_MAX 0u  // lane-parallel pass 2 up to this many entries: measured slower than the loop (see its note)
 #endif
     template <bool GLOBAL>
     __device__ bool pass2_on(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane, uint32_t serial_below) {
-        if (!GLOBAL && nstack <= MR_PASS2_PAR_MAX && nstack > 0u) {
+        if (!GLOBAL && nstack <= MR_PASS2_SMALL_MAX && nstack > 0u) {
+            int r;
+            switch (nstack) {
+                case 1: r = pass2_small<1>(p1, up, lo); break;
+                case 2: r = pass2_small<2>(p1, up, lo); break;
+                case 3: r = pass2_small<3>(p1, up, lo); break;
+                default: r = pass2_small<4>(p1, up, lo); break;
+            }
+            if (r >= 0) return r != 0;
+        } else if (!GLOBAL && nstack <= MR_PASS2_PAR_MAX && nstack > 0u) {
             const int r = pass2_parallel(p1, up, lo, lane);
             if (r >= 0) return r != 0;
         }
