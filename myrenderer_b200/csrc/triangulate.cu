@@ -1668,7 +1668,7 @@ int mr_triangulate_small(mr_context* ctx, const mr_polygon_job* jp, int* rc_out)
     const size_t out_end = o;
     const size_t o_spec = o;  o += up16((size_t)npoly * 4);   // device only
     const size_t o_gen = o;   o += up16((size_t)npoly * 4);   // device only
-    if (npts > (1u << 20) || o > SMALL_MAX_BYTES) return 0;
+    if (npts > (1u << 20) || ntri > (1u << 20) || o > SMALL_MAX_BYTES) return 0;  // (also catches non-monotonic offsets)
 
     auto fail = [&](int rc) { *rc_out = rc; return 1; };
     PolyPlan* plan = nullptr;

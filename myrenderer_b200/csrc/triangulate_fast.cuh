@@ -1240,7 +1240,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
 #define MR_TEAM_LOC_DIV 64u
 #endif
 #ifndef MR_TEAM_ITEM_MULT
-#define MR_TEAM_ITEM_MULT 4u
+#define MR_TEAM_ITEM_MULT 3u
 #endif
     // the caches are refreshed every refresh_every edges, the conflict lists every item_mult-th refresh (single warp:
     // measured best of 1/2/4/8 on n <= 1024); countdowns instead of `at % period` (a run-time modulo per edge)
