@@ -277,9 +277,10 @@ typedef struct mr_polygon_job {
 int mr_triangulate_batch(mr_context* ctx, const mr_polygon_job* job);
 /* Introspection: how the last mr_triangulate_batch on this context spread its polygons over the
  * arena tiers.  out[0..4] = polygons re-run with contract-cap arenas, by size (<=64, <=128, <=256,
- * <=512, <=1024 points); out[5] = 0 (reserved); out[6] = polygons handed to the general path
- * (coincident points, not-acute corner, ...); out[7] = polygons of 1025..MR_MAX_POLYGON_POINTS
- * points (always general path).  Synchronises the stream. */
+ * <=512, <=1024 points); out[5] = polygons of 1025..3072 points handed from their shared-memory
+ * pass to the general path (there is no retry tier at that size); out[6] = polygons of up to 1024
+ * points handed to the general path (coincident points, not-acute corner, ...); out[7] = polygons
+ * of 3073..MR_MAX_POLYGON_POINTS points (always general path).  Synchronises the stream. */
 int mr_triangulate_tier_counts(mr_context* ctx, uint32_t out[8]);
 /* first_tri[0..npoly] from first_point[0..npoly] (device or host pointers). */
 int mr_polygon_offsets(mr_context* ctx, const uint64_t* first_point, uint32_t npoly,

@@ -25,14 +25,17 @@ namespace {
 
 constexpr uint32_t NIL = 0xFFFFu;
 enum : uint32_t { T_POINT = 0, T_SEGMENT = 1, T_TRAPEZOID = 2 };
-constexpr int NUM_CLASSES = 11;  // classes 0..9: shared-memory workspaces (see class_nmax); 10: up to MR_MAX (global memory)
+constexpr int NUM_CLASSES = 12;  // classes 0..10: shared-memory workspaces (see class_nmax); 11: up to MR_MAX (global memory)
+constexpr int XL_CLASS = 10;     // 1025..3072 points: one polygon per SM; no contract-cap tier fits shared memory, so a
+                                 // polygon that outgrows the typical-case arenas goes to the global-memory general path
 constexpr int CLASS_SLOTS = 16; // header words reserved per per-class array
 constexpr int NBINS = MR_MAX_POLYGON_POINTS + 1;  // polygons are queued by exact size, largest first
 constexpr int MAX_WARPS_PER_BLOCK = 4;
 
 // Largest polygon of shared-memory class c.  Above 64 points a class is bound by the polygons whose workspaces
 // (~73 bytes per point, fast_layout) fit the SM's 228 KB, so the boundaries sit where one more polygon fits:
-// 1024 points -> 3 per SM, 768 -> 4, 608 -> 5, 504 -> 6, 368 -> 8, 288 -> 10, 216 -> 13, 168 -> 16, 128 -> 20.
+// 1024 points -> 3 per SM, 768 -> 4, 608 -> 5, 504 -> 6, 368 -> 8, 288 -> 10, 216 -> 13, 168 -> 16, 128 -> 20;
+// 3072 points (220 KB) -> one per SM.
 __host__ __device__ inline uint32_t class_nmax(int c) {
     switch (c) {
         case 0: return 64u;
@@ -44,7 +47,8 @@ __host__ __device__ inline uint32_t class_nmax(int c) {
         case 6: return 504u;
         case 7: return 608u;
         case 8: return 768u;
-        default: return 1024u;
+        case 9: return 1024u;
+        default: return 3072u;
     }
 }
 // warps cooperating on one polygon in the first (typical-case) pass of class c; 1 = independent warps
@@ -52,7 +56,7 @@ __host__ __device__ inline uint32_t class_nmax(int c) {
 // points independent warps; too wide a team loses polygons in flight to the register file)
 inline int team_warps(int c) {  // keep in step with the kernel tables in mr_triangulate_impl
     const uint32_t nmax = class_nmax(c);
-    return nmax <= 288u ? 1 : nmax == 368u ? 3 : nmax <= 608u ? 4 : nmax == 768u ? 6 : 8;
+    return nmax <= 288u ? 1 : nmax == 368u ? 3 : nmax <= 608u ? 4 : nmax == 768u ? 6 : 8;  // 1024 and 3072: 8
 }
 __host__ __device__ inline int class_of(uint32_t n) {
     int c = 0;
@@ -1130,7 +1134,9 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
             if (rc == F_DONE) {
                 write_result(a, pi, r);
             } else if (lane == 0) {
-                if (rc == F_REQUEUE_SPEC)
+                // (the XL class has no contract-cap tier: both kinds of hand-over go to its slice of spec_list, which
+                // the global-memory general kernel of the > 1024-point polygons consumes)
+                if (rc == F_REQUEUE_SPEC || c == XL_CLASS)
                     a.spec_list[begin + atomicAdd(&a.spec_count[c], 1u)] = pi;
                 else
                     a.general_list[atomicAdd(a.general_count, 1u)] = pi;
@@ -1143,7 +1149,8 @@ __global__ void __launch_bounds__(W * 32) triangulate_team_k(const BatchArgs a, 
 
 // General path (float compares, 12-byte nodes, literal fallback loop), global-memory workspace:
 // which == 0: polygons handed over by the fast path (coincident points, not-acute corner, oversized
-// mountain lists; n <= 1024); which == 1: the last class (1024 < n <= MR_MAX_POLYGON_POINTS).
+// mountain lists; n <= 1024); which == 1: the last class (3072 < n <= MR_MAX_POLYGON_POINTS), then the polygons the
+// XL class (1025..3072) handed over.
 __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_general_k(const BatchArgs a, uint32_t nmax, int which) {
     const Caps caps = tier1_caps(nmax);
     const WsLayout L = ws_layout(caps, false);
@@ -1152,13 +1159,15 @@ __global__ void __launch_bounds__(MAX_WARPS_PER_BLOCK * 32) triangulate_general_
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t c = NUM_CLASSES - 1;
     const uint32_t begin = a.class_begin[c], end = a.class_end[c];
-    const uint32_t total = which == 0 ? *a.general_count : (end - begin);
+    const uint32_t xl_begin = a.class_begin[XL_CLASS];
+    const uint32_t total = which == 0 ? *a.general_count : (end - begin) + a.spec_count[XL_CLASS];
     for (;;) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(&a.queue_head[2 * NUM_CLASSES + which], 1u);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= total) break;
-        const uint32_t pi = which == 0 ? a.general_list[idx] : a.order[begin + idx];
+        const uint32_t pi = which == 0 ? a.general_list[idx]
+                                       : (idx < end - begin ? a.order[begin + idx] : a.spec_list[xl_begin + (idx - (end - begin))]);
         Result r;
         process_polygon(a, pi, ws, caps, L, true, &r);
         write_result(a, pi, r);
@@ -1343,11 +1352,11 @@ int mr_triangulate_tier_counts_impl(mr_context* ctx, uint32_t out[8]) {
     // spec_count per internal class, folded into the documented size tiers <=64, <=128, <=256, <=512, <=1024
     for (int c = 0; c < NUM_CLASSES - 1; ++c) {
         const uint32_t nmax = class_nmax(c);
-        const int tier = nmax <= 64u ? 0 : nmax <= 128u ? 1 : nmax <= 256u ? 2 : nmax <= 512u ? 3 : 4;
-        out[tier] += hdr[HDR_SPEC_COUNT + c];
+        const int tier = nmax <= 64u ? 0 : nmax <= 128u ? 1 : nmax <= 256u ? 2 : nmax <= 512u ? 3 : nmax <= 1024u ? 4 : 5;
+        out[tier] += hdr[HDR_SPEC_COUNT + c];  // (tier 5, 1025..3072 points: handed to the general path, there is no retry tier)
     }
     out[6] = hdr[HDR_GENERAL_COUNT];
-    out[7] = hdr[HDR_CLASS_END + NUM_CLASSES - 1] - hdr[HDR_CLASS_BEGIN + NUM_CLASSES - 1];  // the > 1024 class
+    out[7] = hdr[HDR_CLASS_END + NUM_CLASSES - 1] - hdr[HDR_CLASS_BEGIN + NUM_CLASSES - 1];  // the > 3072 class
     return MR_OK;
 }
 
@@ -1372,6 +1381,10 @@ int build_plan(mr_context* ctx, PolyPlan* plan) {
             ClassLaunch& out = spec ? plan->spec[c] : plan->first[c];
             const FCaps caps = fast_caps(c, spec != 0);
             const FLayout L = fast_layout(caps);
+            if (spec && c == XL_CLASS) {  // contract-cap arenas of a 3072-point polygon do not fit shared memory
+                out = {nullptr, 1, 1, 0, 0};
+                continue;
+            }
             if (!fast_layout_ok(caps, L)) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace layout is inconsistent");
             if (L.total > ctx->smem_optin) return mr_fail(ctx, MR_E_CUDA, "fast-path workspace exceeds shared memory");
             const int team = spec ? 1 : team_warps(c);
@@ -1502,7 +1515,7 @@ int class0_scratch(mr_context* ctx, const PolyPlan& plan, BatchArgs& a) {
 // general path: global-memory workspaces, one per warp of the grid.  which == 0: polygons handed over by the fast
 // path; which == 1: the 1025..MR_MAX_POLYGON_POINTS class.
 int launch_general(mr_context* ctx, BatchArgs& a, int which, uint32_t units) {
-    const uint32_t nmax = which == 0 ? class_nmax(NUM_CLASSES - 2) : MR_MAX_POLYGON_POINTS;
+    const uint32_t nmax = which == 0 ? class_nmax(XL_CLASS - 1) : MR_MAX_POLYGON_POINTS;
     const Caps c1 = tier1_caps(nmax);
     const WsLayout L1 = ws_layout(c1, false);
     const int wpb = which == 0 ? 4 : 1;
@@ -1588,7 +1601,7 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j, const uint64_t
     int first_error = MR_OK;
     bool forked[NUM_CLASSES - 1] = {false};
     for (int c = 0; c < NUM_CLASSES - 1 && !first_error; ++c) {
-        if (!count[c]) continue;
+        if (!count[c] || !plan->spec[c].kern) continue;
         cudaStream_t st = ctx->aux[c];
         if (cudaStreamWaitEvent(st, ctx->fork_ev, 0) != cudaSuccess) { first_error = mr_fail(ctx, MR_E_CUDA, "cudaStreamWaitEvent"); break; }
         forked[c] = true;
@@ -1602,13 +1615,13 @@ int mr_triangulate_impl(mr_context* ctx, const mr_polygon_job* j, const uint64_t
     if (first_error) return first_error;
     // general path
     uint32_t shared_total = 0;
-    for (int c = 0; c < NUM_CLASSES - 1; ++c) shared_total += count[c];
+    for (int c = 0; c < XL_CLASS; ++c) shared_total += count[c];
     if (shared_total) {
         rc = launch_general(ctx, a, 0, first_point_host ? shared_total : npoly);
         if (rc) return rc;
     }
-    if (count[NUM_CLASSES - 1]) {
-        rc = launch_general(ctx, a, 1, count[NUM_CLASSES - 1]);
+    if (count[NUM_CLASSES - 1] || count[XL_CLASS]) {
+        rc = launch_general(ctx, a, 1, first_point_host ? count[NUM_CLASSES - 1] + count[XL_CLASS] : npoly);
         if (rc) return rc;
     }
     return MR_OK;
@@ -1711,7 +1724,7 @@ int mr_triangulate_small(mr_context* ctx, const mr_polygon_job* jp, int* rc_out)
     {   // queue order: class by class; inside a class largest first (stable counting sort on the size, like size_scatter_k
         // up to the order among equal sizes, which does not affect results)
         uint32_t begin[NUM_CLASSES], run = 0;
-        for (int c = NUM_CLASSES - 1; c >= 0; --c) {  // descending sizes overall: class 10 first, like the device sort
+        for (int c = NUM_CLASSES - 1; c >= 0; --c) {  // descending sizes overall: the last class first, like the device sort
             begin[c] = run;
             hdr[HDR_CLASS_BEGIN + c] = run;
             run += count[c];
@@ -1750,8 +1763,8 @@ int mr_triangulate_small(mr_context* ctx, const mr_polygon_job* jp, int* rc_out)
         rc = launch_class(ctx, plan->first[c], a, c, 0, ctx->stream, count[c]);
         if (rc) return fail(rc);
     }
-    if (count[NUM_CLASSES - 1]) {
-        rc = launch_general(ctx, a, 1, count[NUM_CLASSES - 1]);
+    if (count[NUM_CLASSES - 1] || count[XL_CLASS]) {  // (the XL class's hand-overs are consumed by the same kernel)
+        rc = launch_general(ctx, a, 1, count[NUM_CLASSES - 1] + count[XL_CLASS]);
         if (rc) return fail(rc);
     }
     auto fetch = [&]() -> int {
@@ -1763,9 +1776,9 @@ int mr_triangulate_small(mr_context* ctx, const mr_polygon_job* jp, int* rc_out)
     if (rc) return fail(rc);
     // ---- rare: polygons that outgrew the first-pass arenas ---------------------------------------------------
     uint32_t respec = 0;
-    for (int c = 0; c < NUM_CLASSES - 1; ++c) respec += hdr[HDR_SPEC_COUNT + c];
+    for (int c = 0; c < XL_CLASS; ++c) respec += hdr[HDR_SPEC_COUNT + c];
     if (respec || hdr[HDR_GENERAL_COUNT]) {
-        for (int c = 0; c < NUM_CLASSES - 1; ++c) {
+        for (int c = 0; c < XL_CLASS; ++c) {
             if (!hdr[HDR_SPEC_COUNT + c]) continue;
             rc = launch_class(ctx, plan->spec[c], a, c, 1, ctx->stream, hdr[HDR_SPEC_COUNT + c]);
             if (rc) return fail(rc);

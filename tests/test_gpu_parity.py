@@ -361,8 +361,8 @@ def _convex(n, rng):
 
 
 def test_size_class_boundaries_convex_and_star(ctx, oracle):
-    """Every size class of the kernel (n <= 64, 128, 168, 216, 288, 368, 504, 608, 768, 1024, then global memory) at
-    its largest size and one past it; several polygons per size so that the persistent warps / warp teams run
+    """Every size class of the kernel (n <= 64, 128, 168, 216, 288, 368, 504, 608, 768, 1024, then the one-per-SM class
+    up to 3072) at its largest size and one past it; several polygons per size so that the persistent warps / warp teams run
     their queue loop, and explicit unirand pairs as well as seeded ones."""
     import myrenderer_b200 as mr
 
@@ -377,7 +377,7 @@ def test_size_class_boundaries_convex_and_star(ctx, oracle):
     tc = (C.c_uint32 * 8)()
     ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
     assert sum(tc[0:7]) == 0, list(tc)            # convex input: everything in the first shared-memory pass
-    assert tc[7] == 3                              # the three 1025-gons ride in the global-memory class
+    assert tc[7] == 0                              # the three 1025-gons run in the 1025..3072 shared-memory class
     # explicit (offset, prime) pairs, incl. prime 1 and the largest table prime below n
     ops = np.array([[1 + (i * 7) % (n - 1), 1 if i % 2 else 3] for i, n in enumerate(sizes)], dtype=np.uint32)
     _check_batch(ctx, oracle, xy, fp, offset_prime=ops)
@@ -767,3 +767,38 @@ def test_terrain_tiles_and_cull_match_oracle(ctx, oracle):
             ctx.check(lib.mr_terrain_cull(ctx.handle, want_box.ctypes.data, n, tr, tc, m.ctypes.data, None, None,
                                           idx_h.ctypes.data, cnt_h.ctypes.data), "cull host")
             assert cnt_h.tolist() == ref["counts"].tolist() and np.array_equal(idx_h[: int(cnt_h[1])], ref["idx"])
+
+
+def test_xl_class_1025_to_3072_points(ctx, oracle):
+    """Polygons of 1025..3072 points run in shared memory too (one polygon per SM, a team of 8 warps); above that, and
+    whenever such a polygon outgrows the typical-case arenas (exploding stars), the global-memory general path takes
+    over.  Bit-exact either way."""
+    sizes = np.array([1025, 1026, 1500, 2047, 2048, 2049, 3000, 3071, 3072, 3073, 4096, 1024, 900])
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    tc = (C.c_uint32 * 8)()
+    for fam in (oracle.FAMILY_ELLIPSE, oracle.FAMILY_ZIPPER):
+        xy = oracle.synth_polygons(0x71A5, fp, family=fam)
+        _, ref = _check_batch(ctx, oracle, xy, fp, seed=0x71A5)
+        assert (ref["status"] == 0).all()
+        ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
+        assert tc[5] == 0 and tc[6] == 0 and tc[7] == 2, list(tc)  # only 3073 and 4096 take the general path
+    # stars of that size explode: handed over, same bytes as the oracle (mostly MR_POLY_ARENA)
+    sizes = np.array([1100, 1300, 2000, 2500, 3072, 1025])
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    xy = oracle.synth_polygons(0x71A6, fp, family=oracle.FAMILY_STAR)
+    _check_batch(ctx, oracle, xy, fp, seed=0x71A6)
+    ctx.check(ctx.lib.mr_triangulate_tier_counts(ctx.handle, tc), "tier counts")
+    assert tc[5] >= 1 and tc[7] == 0, list(tc)
+    # host pointers: the small-batch path schedules the same classes
+    import myrenderer_b200 as mr
+
+    P = mr.Polygon(ctx)
+    sizes = np.array([2048, 7, 3073, 1025])
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    xy = oracle.synth_polygons(0x71A7, fp, family=oracle.FAMILY_ZIPPER)
+    ref = oracle.polygon_batch(xy, fp, seed=0x71A7, nthreads=0)
+    ft = ref["first_tri"]
+    vtx = np.zeros(int(ft[-1]) * 96, dtype=np.uint8)
+    st = np.zeros(4, dtype=np.uint32)
+    P.triangulate(P.job(xy, fp, 4, vtx_out=vtx, first_tri=ft, status_out=st, seed=0x71A7))
+    assert np.array_equal(st, ref["status"]) and np.array_equal(vtx, ref["vtx"])
