@@ -458,6 +458,36 @@ def main():
     ms_c = sum(x.elapsed_time(y) for x, y in tc) / len(tc)
     ok_c = int((cstat == 0).sum().item())
 
+    # ---- terrain tiles: bounding boxes + the reference's visibility test with compaction -------
+    cull = None
+    if world == 1:
+        tile = 64
+        tr_, tc_ = C.c_uint32(), C.c_uint32()
+        lib.mr_terrain_tile_count(n, tile, tile, C.byref(tr_), C.byref(tc_))
+        ntiles = tr_.value * tc_.value
+        boxes = torch.empty(ntiles * 8, dtype=torch.float32, device=dev)
+        cidx = torch.empty(6 * (n - 1) * (n - 1), dtype=torch.int32, device=dev)
+        ccnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        # q = (x, y + 1, z, 1): a tile passes iff its box reaches into the quadrant x > 0, z > 0 (about a quarter of them)
+        m = np.ascontiguousarray(np.array([[1, 0, 0, 0], [0, 1, 0, 1], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float32).T.reshape(16))
+
+        def do_bounds():
+            ctx.check(lib.mr_terrain_tile_bounds(ctx.handle, height.data_ptr(), 0, n, tile, tile, None, boxes.data_ptr()), "tile bounds")
+
+        def do_cull():
+            ctx.check(lib.mr_terrain_cull(ctx.handle, boxes.data_ptr(), n, tile, tile, m.ctypes.data, None, None, cidx.data_ptr(),
+                                          ccnt.data_ptr()), "cull")
+
+        ms_tb = timed(do_bounds, reps=10, warm=2)
+        ms_cu = timed(do_cull, reps=10, warm=2)
+        cc = ccnt.cpu().numpy()
+        cull = {"tile_quads": tile, "tiles": int(ntiles), "tile_bounds_us": ms_tb * 1e3, "cull_us": ms_cu * 1e3,
+                "visible_tiles": int(cc[0]), "indices_written": int(cc[1]),
+                "index_write_gb_per_s": int(cc[1]) * 4 / (ms_cu * 1e-3) / 1e9,
+                "what": "mr_terrain_tile_bounds (per-tile min/max, reads the u16 heightmap once) and mr_terrain_cull "
+                        "(SceneNode.zig:96-110 per tile + ordered compaction + compacted index buffer)"}
+        del boxes, cidx
+
     # ---- end to end through the C ABI with pinned host buffers --------------------------------
     e2e = None
     if not args.no_e2e:
@@ -649,6 +679,8 @@ def main():
                            "pcie_floor_ms": e_floor, "fraction_of_pcie_floor": e_floor / e_ms_t,
                            "path": "mr_terrain_build / mr_triangulate_batch with pinned host buffers; pcie_floor_ms = the "
                                    "terrain call's bytes moved by plain pinned copies (both directions at once)"}
+        if cull is not None:
+            line["terrain_cull"] = cull
         if single is not None:
             line["single_polygon_us"] = single["us"]
             line["single_polygon"] = single

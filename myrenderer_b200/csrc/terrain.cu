@@ -312,6 +312,82 @@ __global__ void __launch_bounds__(256) terrain_tile_bounds_k(const TileArgs a) {
     }
 }
 
+// The same for tiles of at most 512 columns, coalesced: a CTA takes a strip of whole tiles (<= 512 columns + the shared
+// boundary column) of one tile row; thread t walks down columns t, t + 256, ... so that every warp load is contiguous,
+// the per-column minima / maxima meet in shared memory and one thread per tile combines its columns.
+constexpr int TB_COLS = 512;
+// PAIR (u16 map, n and tile_cols even, 4-byte aligned base): a thread owns two adjacent columns and loads both texels
+// with one 32-bit load (128 contiguous bytes per warp instruction); the odd boundary column is read on its own.
+template <bool U16, bool PAIR>
+__global__ void __launch_bounds__(256) terrain_tile_bounds_strip_k(const TileArgs a, uint32_t tiles_per_cta) {
+    __shared__ float cmin[TB_COLS + 2], cmax[TB_COLS + 2];
+    const uint32_t tr = blockIdx.y, tc0 = blockIdx.x * tiles_per_cta;
+    const uint32_t r0 = tr * a.tile_rows, r1 = min(r0 + a.tile_rows, a.n - 1u);
+    const uint32_t c_begin = tc0 * a.tile_cols;
+    const uint32_t c_end = min(c_begin + tiles_per_cta * a.tile_cols, a.n - 1u);  // inclusive
+    const float pinf = __uint_as_float(0x7F800000u), ninf = __uint_as_float(0xFF800000u);
+    if (PAIR) {
+        const uint32_t ncols = c_end - c_begin + 1u;
+        const uint16_t* h16 = static_cast<const uint16_t*>(a.height);
+        for (uint32_t p = threadIdx.x; 2u * p + 1u < ncols; p += blockDim.x) {
+            float lo0 = pinf, hi0 = ninf, lo1 = pinf, hi1 = ninf;
+#pragma unroll 8
+            for (uint32_t r = r0; r <= r1; ++r) {
+                const uint32_t two = __ldg(reinterpret_cast<const uint32_t*>(h16 + (size_t)r * a.n + c_begin + 2u * p));
+                const float v0 = height_from_u16(two & 0xFFFFu), v1 = height_from_u16(two >> 16);
+                lo0 = v0 < lo0 ? v0 : lo0;
+                hi0 = v0 > hi0 ? v0 : hi0;
+                lo1 = v1 < lo1 ? v1 : lo1;
+                hi1 = v1 > hi1 ? v1 : hi1;
+            }
+            cmin[2u * p] = lo0;
+            cmax[2u * p] = hi0;
+            cmin[2u * p + 1u] = lo1;
+            cmax[2u * p + 1u] = hi1;
+        }
+        if ((ncols & 1u) && threadIdx.x == blockDim.x - 1u) {  // the boundary column shared with the next strip
+            float lo = pinf, hi = ninf;
+            for (uint32_t r = r0; r <= r1; ++r) {
+                const float v = load_height<true>(a.height, (size_t)r * a.n + c_end);
+                lo = v < lo ? v : lo;
+                hi = v > hi ? v : hi;
+            }
+            cmin[ncols - 1u] = lo;
+            cmax[ncols - 1u] = hi;
+        }
+    } else {
+        for (uint32_t c = c_begin + threadIdx.x; c <= c_end; c += blockDim.x) {
+            float lo = pinf, hi = ninf;
+#pragma unroll 8
+            for (uint32_t r = r0; r <= r1; ++r) {
+                const float v = load_height<U16>(a.height, (size_t)r * a.n + c);
+                lo = v < lo ? v : lo;
+                hi = v > hi ? v : hi;
+            }
+            cmin[c - c_begin] = lo;
+            cmax[c - c_begin] = hi;
+        }
+    }
+    __syncthreads();
+    const uint32_t tc = tc0 + threadIdx.x;
+    if (threadIdx.x < tiles_per_cta && tc < a.tiles_c) {
+        const uint32_t c0 = tc * a.tile_cols, c1 = min(c0 + a.tile_cols, a.n - 1u);
+        float lo = __uint_as_float(0x7F800000u), hi = __uint_as_float(0xFF800000u);
+        for (uint32_t c = c0; c <= c1; ++c) {
+            const float l = cmin[c - c_begin], h = cmax[c - c_begin];
+            lo = l < lo ? l : lo;
+            hi = h > hi ? h : hi;
+        }
+        const float org = __fmul_rn(a.origin_scale, (float)a.n);
+        const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
+        const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
+        const float ya = __fmul_rn(a.height_scale, lo), yb = __fmul_rn(a.height_scale, hi);
+        float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * ((size_t)tr * a.tiles_c + tc));
+        o[0] = make_float4(fminf(xa, xb), fminf(ya, yb), fminf(za, zb), 1.0f);
+        o[1] = make_float4(fmaxf(xa, xb), fmaxf(ya, yb), fmaxf(za, zb), 1.0f);
+    }
+}
+
 // mach.math Mat4x4.mulVec: result[i] = 0; for j in 0..3: result[i] += m[j][i] * v[j]   (every operation rounded)
 __device__ __forceinline__ float4 mach_mul_vec(const float* m, const float4 v) {
     const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -420,22 +496,52 @@ __global__ void __launch_bounds__(1024) terrain_cull_k(const CullArgs a) {
     }
 }
 
-// compacted index buffer: CTA k writes visible tile k (CTAs beyond the visible count leave at once)
-__global__ void __launch_bounds__(256) terrain_cull_indices_k(const CullArgs a, uint32_t* __restrict__ idx_out) {
+// compacted index buffer: CTA (k, chunk) writes TI_QUADS quads of visible tile k -- the tile's quads are one contiguous
+// run of the output -- built in shared memory and shipped with one bulk async copy, like terrain_indices_k (CTAs beyond
+// the visible count leave at once)
+__global__ void __launch_bounds__(TI_THREADS) terrain_cull_indices_k(const CullArgs a, uint32_t* __restrict__ idx_out) {
+    __shared__ __align__(16) uint32_t buf[TI_QUADS * 6 + 4];
     if (blockIdx.x >= a.counts[0]) return;
     const uint32_t t = a.visible_ids[blockIdx.x];
     const uint32_t tr = t / a.tiles_c, tc = t - tr * a.tiles_c;
     const uint32_t r0 = tr * a.tile_rows, c0 = tc * a.tile_cols;
     const uint32_t qr = min(a.tile_rows, a.n - 1u - r0), qc = min(a.tile_cols, a.n - 1u - c0);
-    uint2* dst = reinterpret_cast<uint2*>(idx_out + a.first_index[blockIdx.x]);  // 24-byte quads: 8-byte aligned
+    const uint32_t q0 = blockIdx.y * TI_QUADS;
+    if (q0 >= qr * qc) return;
+    const uint32_t nq = min((uint32_t)TI_QUADS, qr * qc - q0);
+    uint32_t* dst = idx_out + a.first_index[blockIdx.x] + (size_t)q0 * 6;  // 24-byte quads: 8-byte aligned
+    const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3u);
+    uint32_t* sbuf = buf + mis;
     const uint32_t n = a.n;
-    for (uint32_t q = threadIdx.x; q < qr * qc; q += blockDim.x) {
-        const uint32_t lr = q / qc, lc = q - lr * qc;
-        const uint32_t i00 = (r0 + lr) * n + c0 + lc;
-        dst[3 * (size_t)q] = make_uint2(i00 + n, i00);
-        dst[3 * (size_t)q + 1] = make_uint2(i00 + n + 1, i00 + n + 1);
-        dst[3 * (size_t)q + 2] = make_uint2(i00, i00 + 1);
+#pragma unroll
+    for (int k = 0; k < TI_QPT; ++k) {
+        const uint32_t ql = k * TI_THREADS + threadIdx.x;
+        if (ql < nq) {
+            const uint32_t q = q0 + ql;
+            const uint32_t lr = q / qc, lc = q - lr * qc;
+            const uint32_t i00 = (r0 + lr) * n + c0 + lc;
+            uint2* sm = reinterpret_cast<uint2*>(sbuf + ql * 6);
+            sm[0] = make_uint2(i00 + n, i00);
+            sm[1] = make_uint2(i00 + n + 1, i00 + n + 1);
+            sm[2] = make_uint2(i00, i00 + 1);
+        }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t words = nq * 6;
+    const uint32_t head = mis ? 2u : 0u;
+    const uint32_t body = ((words - head) / 4u) * 4u;
+    if (threadIdx.x == 0 && body) {
+        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sbuf + head);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head), "r"(saddr), "r"(body * 4u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        if (head) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(sbuf);
+        if (words - head - body) *reinterpret_cast<uint2*>(dst + head + body) = *reinterpret_cast<uint2*>(sbuf + head + body);
+    }
+    if (threadIdx.x == 0 && body) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // exhaustive check of div_const against __fdiv_rn over all 2^32 dividends
@@ -550,11 +656,24 @@ int mr_terrain_tile_bounds_impl(mr_context* ctx, const void* height_dev, uint32_
     a.origin_scale = p->origin_scale;
     a.height_scale = p->height_scale;
     a.bbox_out = bbox_dev;
-    const unsigned grid = tiles_r * a.tiles_c;
-    if (height_fmt == MR_HEIGHT_U16)
-        terrain_tile_bounds_k<true><<<grid, 256, 0, ctx->stream>>>(a);
-    else
-        terrain_tile_bounds_k<false><<<grid, 256, 0, ctx->stream>>>(a);
+    if (tile_cols <= (uint32_t)TB_COLS && tiles_r <= 65535u) {  // coalesced strips of whole tiles
+        const uint32_t per = std::max(1u, (uint32_t)TB_COLS / tile_cols);
+        const dim3 grid((a.tiles_c + per - 1u) / per, tiles_r);
+        const bool pair = height_fmt == MR_HEIGHT_U16 && (n & 1u) == 0u && (tile_cols & 1u) == 0u &&
+                          (reinterpret_cast<uintptr_t>(height_dev) & 3u) == 0u;
+        if (pair)
+            terrain_tile_bounds_strip_k<true, true><<<grid, 256, 0, ctx->stream>>>(a, per);
+        else if (height_fmt == MR_HEIGHT_U16)
+            terrain_tile_bounds_strip_k<true, false><<<grid, 256, 0, ctx->stream>>>(a, per);
+        else
+            terrain_tile_bounds_strip_k<false, false><<<grid, 256, 0, ctx->stream>>>(a, per);
+    } else {
+        const unsigned grid = tiles_r * a.tiles_c;
+        if (height_fmt == MR_HEIGHT_U16)
+            terrain_tile_bounds_k<true><<<grid, 256, 0, ctx->stream>>>(a);
+        else
+            terrain_tile_bounds_k<false><<<grid, 256, 0, ctx->stream>>>(a);
+    }
     MR_LAUNCH_CHECK(ctx, "terrain_tile_bounds_k");
     return MR_OK;
 }
@@ -578,7 +697,10 @@ int mr_terrain_cull_impl(mr_context* ctx, const float* bbox_dev, uint32_t n, uin
     terrain_cull_k<<<1, 1024, 0, ctx->stream>>>(a);
     MR_LAUNCH_CHECK(ctx, "terrain_cull_k");
     if (idx_dev) {
-        terrain_cull_indices_k<<<a.ntiles, 256, 0, ctx->stream>>>(a, idx_dev);
+        const uint64_t tile_quads = (uint64_t)std::min(tile_rows, n - 1u) * std::min(tile_cols, n - 1u);
+        const uint64_t chunks = (tile_quads + TI_QUADS - 1) / TI_QUADS;
+        if (chunks > 65535u) return mr_fail(ctx, MR_E_BADARG, "cull: tiles too large for one launch");
+        terrain_cull_indices_k<<<dim3(a.ntiles, (unsigned)chunks), TI_THREADS, 0, ctx->stream>>>(a, idx_dev);
         MR_LAUNCH_CHECK(ctx, "terrain_cull_indices_k");
     }
     return MR_OK;
