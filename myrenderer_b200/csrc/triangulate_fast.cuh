@@ -500,11 +500,10 @@ struct FPoly {
     // the previous step that closed the same side): all steps can run at once.  Returns 1 done, 0 failed (status /
     // requeue set as the loop would), -1 when the conditions do not hold (duplicates, null lower points, ...): the
     // caller then runs the loop as written.
-    // MEASURED (round 2, B200): the single-entry case (the segment stays inside one trapezoid, about a third of the
-    // edges of a convex polygon) gains 1.3-2.4 % on the 8..1024-point batches; for 2..32 entries the lane-parallel
-    // form is bit-exact (the whole parity suite passes with MR_PASS2_PAR_MAX = 32) but 4-8 % SLOWER than the loop --
-    // with the 2-3 entries of sound input the ballots, MATCH and shuffle loops cost more than they save -- so it is
-    // compiled for one entry only.
+    // MEASURED (round 2, B200): bit-exact (the whole parity suite passes with MR_PASS2_PAR_MAX = 32) but 4-8 % SLOWER than
+    // the loop on the 8..1024-point batches -- with the 2-3 entries of sound input the ballots, MATCH and shuffle loops
+    // cost more than they save.  Stacks of one and two entries take pass2_small instead; this form is kept behind
+    // MR_PASS2_PAR_MAX (default 0: off) for inputs with long stacks.
     __device__ __forceinline__ int pass2_parallel(uint32_t p1, uint32_t up, uint32_t lo, uint32_t lane) {
         const uint32_t k = nstack;
         const uint32_t A = nnodes;
