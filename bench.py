@@ -74,6 +74,18 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_info():
+    """What the end-to-end numbers at N > 1 are bound by: the box's host side (NUMA nodes, CPUs)."""
+    nodes = None
+    try:
+        txt = open("/sys/devices/system/node/online").read().strip()  # e.g. "0" or "0-1"
+        nodes = sum((int(b) - int(a) + 1) if "-" in part else 1
+                    for part in txt.split(",") for a, _, b in [part.partition("-")])
+    except Exception:
+        pass
+    return {"numa_nodes": nodes, "cpus": os.cpu_count()}
+
+
 def fresh_traffic():
     """DRAM bytes per launch of the vertex kernel from an `ncu --set full` capture -- only when the capture was
     taken from THIS terrain.cu (the file's sha256 is stored beside it); otherwise None."""
@@ -676,7 +688,7 @@ def main():
             line["e2e"] = {"value": verts_total / (e_ms_t * 1e-3) / 1e6, "unit": "Mverts/s",
                            "h2d_bytes_per_step": e_h2d, "d2h_bytes_per_step": e_d2h, "ms_terrain": e_ms_t,
                            "ms_polygons": e_ms_p, "polygons_per_s": polys_total / (e_ms_p * 1e-3),
-                           "pcie_floor_ms": e_floor, "fraction_of_pcie_floor": e_floor / e_ms_t,
+                           "pcie_floor_ms": e_floor, "fraction_of_pcie_floor": e_floor / e_ms_t, "host": host_info(),
                            "path": "mr_terrain_build / mr_triangulate_batch with pinned host buffers; pcie_floor_ms = the "
                                    "terrain call's bytes moved by plain pinned copies (both directions at once)"}
         if cull is not None:
