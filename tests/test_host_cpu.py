@@ -62,3 +62,12 @@ def test_png_loader_matches_fixture():
     h = mr.load_heightmap_png(ref_png)
     want = np.load(os.path.join(os.path.dirname(__file__), "golden", "heightmap_100.npy"))
     assert h.dtype == np.uint16 and np.array_equal(h, want)
+
+
+def test_roofline_traffic_evidence_is_not_stale():
+    """bench.py reports `roofline.traffic` from profiles/r03_traffic.json only while that capture belongs to the
+    committed terrain.cu (sha256 stored beside it); this keeps the two from drifting apart unnoticed."""
+    import bench
+
+    traffic, src = bench.fresh_traffic()
+    assert traffic is not None and 0.5 * 570425344 < traffic < 1.5 * 570425344, "re-capture the vertex kernel: terrain.cu changed"
