@@ -625,9 +625,17 @@ def main():
 
     cfg4 = cfg5 = None
     if not args.no_configs45:
-        cfg4 = run_config4(ctx, T, dev, rank, world, timed, shared_buffer, release, want_gather, checksum, barrier)
+        # (an exception in one of these legs must not cost the headline line; at N > 1 a one-sided failure would
+        # still desynchronise the ranks, so the legs only catch what every rank hits alike, e.g. out of memory)
+        try:
+            cfg4 = run_config4(ctx, T, dev, rank, world, timed, shared_buffer, release, want_gather, checksum, barrier)
+        except Exception as exc:
+            cfg4 = {"error": str(exc)[:200]}
         torch.cuda.empty_cache()
-        cfg5 = run_config5(ctx, P, dev, rank, world, timed, shared_buffer, release, want_gather, reduce_sum)
+        try:
+            cfg5 = run_config5(ctx, P, dev, rank, world, timed, shared_buffer, release, want_gather, reduce_sum)
+        except Exception as exc:
+            cfg5 = {"error": str(exc)[:200]}
         torch.cuda.empty_cache()
 
     # ---- reduce over ranks: max time, sum of units ------------------------------------------------
