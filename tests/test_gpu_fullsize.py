@@ -119,3 +119,57 @@ def test_polygons_1m_skewed_sizes(ctx, oracle):
         t0, t1 = int(batch.first_tri[i]), int(batch.first_tri[i + 1])
         assert np.array_equal(Vb[t0 * 96:t1 * 96].cpu().numpy(), ref["vtx"]), f"polygon {i} (n={z - a})"
         assert np.array_equal(batch.bbox[i].cpu().numpy().view(np.uint32), ref["bbox"].view(np.uint32)[0])
+
+
+def test_polygons_1m_zipper_family(ctx, oracle):
+    """Config 5 with the NON-CONVEX family on which the reference is sound (MR_FAMILY_ZIPPER), generated on the device:
+    all 1,000,000 polygons end OK with n-2 triangles whose areas add up to the polygon's area; a random sample --
+    inputs regenerated on the CPU from the same counter hash -- is compared with the oracle bit for bit."""
+    import torch
+
+    import myrenderer_b200 as mr
+
+    npoly = 1_000_000
+    seed = 0x5EED0005
+    fp = oracle.synth_polygon_sizes(seed, npoly, 8, 1024, dist=1)
+    npts = int(fp[-1])
+    fpd = torch.from_numpy(fp.astype(np.int64)).cuda()
+    xy = torch.empty(npts * 2, dtype=torch.float32, device="cuda")
+    ctx.check(ctx.lib.mr_synth_polygons_family(ctx.handle, oracle.FAMILY_ZIPPER, seed, 0, fpd.data_ptr(), npoly, xy.data_ptr()), "synth")
+    xy = xy.view(-1, 2)
+    P = mr.Polygon(ctx)
+    batch = P.create_polygons(xy, fp, seed=seed)
+    ctx.sync()
+    status = batch.status.cpu().numpy().view(np.uint32)
+    n = np.diff(fp.astype(np.int64))
+    assert (status == 0).all(), f"statuses: {np.unique(status, return_counts=True)}"
+    assert np.array_equal(batch.ntri.cpu().numpy().view(np.uint32), (n - 2).astype(np.uint32))
+    # areas: sum over each polygon's triangles == shoelace area
+    pid = torch.repeat_interleave(torch.arange(npoly, device="cuda"), fpd[1:] - fpd[:-1])
+    X = xy.double()
+    nxt = torch.arange(npts, device="cuda") + 1
+    nxt[fpd[1:] - 1] = fpd[:-1]
+    cross = X[:, 0] * X[nxt, 1] - X[nxt, 0] * X[:, 1]
+    poly_area = torch.zeros(npoly, device="cuda", dtype=torch.float64).index_add_(0, pid, cross) * 0.5
+    del cross, nxt, pid, X
+    ft = torch.from_numpy(batch.first_tri.astype(np.int64)).cuda()
+    tri_area_sum = torch.zeros(npoly, device="cuda", dtype=torch.float64)
+    Vb = batch.vertex_buffer
+    chunk = 100_000
+    for a in range(0, npoly, chunk):
+        z = min(a + chunk, npoly)
+        t0, t1 = int(ft[a]), int(ft[z])
+        v = Vb[t0 * 96:t1 * 96].view(torch.float32).view(-1, 3, 8)[:, :, :2].double()
+        ar = 0.5 * ((v[:, 1, 0] - v[:, 0, 0]) * (v[:, 2, 1] - v[:, 0, 1]) - (v[:, 2, 0] - v[:, 0, 0]) * (v[:, 1, 1] - v[:, 0, 1]))
+        owner = torch.repeat_interleave(torch.arange(a, z, device="cuda"), ft[a + 1:z + 1] - ft[a:z])
+        tri_area_sum.index_add_(0, owner, ar.abs())
+    rel = ((tri_area_sum - poly_area).abs() / poly_area).max().item()
+    assert rel < 1e-5, rel  # the triangles tile the polygon
+    rng = np.random.default_rng(8)
+    for i in rng.choice(npoly, 400, replace=False):
+        a, z = int(fp[i]), int(fp[i + 1])
+        pts = oracle.synth_polygons(seed, np.array([0, z - a], dtype=np.uint64), poly_index0=int(i), family=oracle.FAMILY_ZIPPER)
+        assert np.array_equal(pts, xy[a:z].cpu().numpy()), f"generator differs at polygon {i}"
+        ref = oracle.polygon_batch(pts, np.array([0, z - a]), seed=seed, poly_index0=int(i), want_ids=False)
+        t0, t1 = int(batch.first_tri[i]), int(batch.first_tri[i + 1])
+        assert np.array_equal(Vb[t0 * 96:t1 * 96].cpu().numpy(), ref["vtx"]), f"polygon {i} (n={z - a})"
