@@ -16,6 +16,8 @@
  *   Triangulation.new / destroy       Polygon/Triangulation.zig:427-440 -> mr_context_create / mr_context_destroy
  *   VertexLayout.native               Renderer/VertexLayout.zig:12-30 -> mr_layout
  *   VertexBuffer{vertex_count,first_vertex}  Renderer/VertexBuffer.zig:5-24 -> mr_draw_range
+ *   SceneNode.render visibility test  Renderer/SceneNode.zig:96-110 -> mr_terrain_cull (per terrain tile)
+ *   Terrain bounding box              Terrain/Terrain.zig:103-110   -> mr_terrain_describe, mr_terrain_tile_bounds
  *
  * Conventions
  *   - plain C types only; no exceptions cross this boundary; every function
