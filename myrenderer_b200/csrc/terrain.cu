@@ -388,6 +388,85 @@ __global__ void __launch_bounds__(256) terrain_tile_bounds_strip_k(const TileArg
     }
 }
 
+// The bandwidth form of the strip kernel (u16 map, n and the strip width multiples of 8, 16-byte aligned base).  The
+// height 1 - v/65535 (Terrain.zig:120) is monotone non-increasing in the texel v, so the minimum height of a tile is the
+// height of its LARGEST texel and vice versa: the reduction runs on the packed u16 pairs (vmaxu2 / vminu2, exact) and
+// only the two results per tile go through the conversion.  A thread takes eight columns with one 128-bit load; four
+// threads share a column group, each taking every fourth row, TB_DEPTH independent loads in flight per thread (rows
+// past the tile repeat its last row, harmless for min / max).
+#ifndef TB_DEPTH
+#define TB_DEPTH 8
+#endif
+__global__ void __launch_bounds__(256) terrain_tile_bounds_wide_k(const TileArgs a, uint32_t tiles_per_cta) {
+    __shared__ __align__(16) uint16_t cmin[4][TB_COLS + 8], cmax[4][TB_COLS + 8];
+    const uint32_t tr = blockIdx.y, tc0 = blockIdx.x * tiles_per_cta;
+    const uint32_t r0 = tr * a.tile_rows, r1 = min(r0 + a.tile_rows, a.n - 1u);
+    const uint32_t c_begin = tc0 * a.tile_cols;
+    const uint32_t c_end = min(c_begin + tiles_per_cta * a.tile_cols, a.n - 1u);  // inclusive
+    const uint32_t ncols = c_end - c_begin + 1u, groups = ncols >> 3;            // ncols % 8 is 0 (right edge) or 1
+    const uint16_t* h16 = static_cast<const uint16_t*>(a.height);
+    const uint32_t tx = threadIdx.x & 63u, ty = threadIdx.x >> 6, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t g = tx; g < groups; g += 64u) {
+        const uint16_t* col = h16 + c_begin + 8u * g;
+        uint4 lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), hi = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t r = r0 + ty; r <= r1; r += 4u * TB_DEPTH) {
+            uint4 q[TB_DEPTH];
+#pragma unroll
+            for (int j = 0; j < TB_DEPTH; ++j)
+                q[j] = __ldg(reinterpret_cast<const uint4*>(col + (size_t)min(r + 4u * j, r1) * a.n));
+#pragma unroll
+            for (int j = 0; j < TB_DEPTH; ++j) {
+                lo.x = __vminu2(lo.x, q[j].x), hi.x = __vmaxu2(hi.x, q[j].x);
+                lo.y = __vminu2(lo.y, q[j].y), hi.y = __vmaxu2(hi.y, q[j].y);
+                lo.z = __vminu2(lo.z, q[j].z), hi.z = __vmaxu2(hi.z, q[j].z);
+                lo.w = __vminu2(lo.w, q[j].w), hi.w = __vmaxu2(hi.w, q[j].w);
+            }
+        }
+        *reinterpret_cast<uint4*>(&cmin[ty][8u * g]) = lo;
+        *reinterpret_cast<uint4*>(&cmax[ty][8u * g]) = hi;
+    }
+    if ((ncols & 7u) && warp == 7u) {  // the boundary column shared with the next strip
+        uint32_t lo = 0xFFFFu, hi = 0u;
+        for (uint32_t r = r0 + lane; r <= r1; r += 32u) {
+            const uint32_t v = __ldg(h16 + (size_t)r * a.n + c_end);
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (lane < 4u) {
+            cmin[lane][ncols - 1u] = (uint16_t)lo;
+            cmax[lane][ncols - 1u] = (uint16_t)hi;
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = warp; t < tiles_per_cta; t += 8u) {
+        const uint32_t tc = tc0 + t;
+        if (tc >= a.tiles_c) break;
+        const uint32_t c0 = tc * a.tile_cols, c1 = min(c0 + a.tile_cols, a.n - 1u);
+        uint32_t lo = 0xFFFFu, hi = 0u;
+        for (uint32_t c = c0 - c_begin + lane; c <= c1 - c_begin; c += 32u) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                lo = min(lo, (uint32_t)cmin[y][c]);
+                hi = max(hi, (uint32_t)cmax[y][c]);
+            }
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (lane == 0u) {
+            const float hmin = height_from_u16(hi), hmax = height_from_u16(lo);
+            const float org = __fmul_rn(a.origin_scale, (float)a.n);
+            const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
+            const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
+            const float ya = __fmul_rn(a.height_scale, hmin), yb = __fmul_rn(a.height_scale, hmax);
+            float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * ((size_t)tr * a.tiles_c + tc));
+            o[0] = make_float4(fminf(xa, xb), fminf(ya, yb), fminf(za, zb), 1.0f);
+            o[1] = make_float4(fmaxf(xa, xb), fmaxf(ya, yb), fmaxf(za, zb), 1.0f);
+        }
+    }
+}
+
 // mach.math Mat4x4.mulVec: result[i] = 0; for j in 0..3: result[i] += m[j][i] * v[j]   (every operation rounded)
 __device__ __forceinline__ float4 mach_mul_vec(const float* m, const float4 v) {
     const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -661,7 +740,11 @@ int mr_terrain_tile_bounds_impl(mr_context* ctx, const void* height_dev, uint32_
         const dim3 grid((a.tiles_c + per - 1u) / per, tiles_r);
         const bool pair = height_fmt == MR_HEIGHT_U16 && (n & 1u) == 0u && (tile_cols & 1u) == 0u &&
                           (reinterpret_cast<uintptr_t>(height_dev) & 3u) == 0u;
-        if (pair)
+        const bool wide = height_fmt == MR_HEIGHT_U16 && (n & 7u) == 0u && ((per * tile_cols) & 7u) == 0u &&
+                          (reinterpret_cast<uintptr_t>(height_dev) & 15u) == 0u;
+        if (wide)
+            terrain_tile_bounds_wide_k<<<grid, 256, 0, ctx->stream>>>(a, per);
+        else if (pair)
             terrain_tile_bounds_strip_k<true, true><<<grid, 256, 0, ctx->stream>>>(a, per);
         else if (height_fmt == MR_HEIGHT_U16)
             terrain_tile_bounds_strip_k<true, false><<<grid, 256, 0, ctx->stream>>>(a, per);

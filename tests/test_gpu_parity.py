@@ -731,7 +731,7 @@ def test_terrain_tiles_and_cull_match_oracle(ctx, oracle):
 
     torch = _torch()
     lib = ctx.lib
-    for n, tr, tc in ((130, 32, 24), (1000, 64, 64), (257, 8, 256), (300, 500, 7)):
+    for n, tr, tc in ((130, 32, 24), (1000, 64, 64), (257, 8, 256), (300, 500, 7), (1024, 33, 16), (264, 64, 24)):  # the last three u16 cases take 128-bit loads
         h = oracle.synth_heightmap_u16(0x5EED0001, n)
         want_box = oracle.terrain_tile_bounds(h, n, tr, tc)
         ntiles = want_box.shape[0]
