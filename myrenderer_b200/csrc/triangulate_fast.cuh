@@ -1401,10 +1401,29 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         }
         uint32_t it = FNIL, it_node0 = 0, it_next0 = FNIL;
         if (use_items) {
-            it = ehead[edge];  // FNIL only when an explicit (offset, prime) pair repeats an edge
+            it = ehead[edge];
             if (it != FNIL) {
                 it_node0 = it_node[it];
                 it_next0 = it_next[it];
+            } else {
+                // An explicit (offset, prime) pair whose prime divides n comes back to an edge it has inserted already
+                // (unirand.zig:16 does not care), and the reference searches and splits again (:493).  The edge's
+                // conflict list was consumed the first time, so the search restarts from a fresh item at the root:
+                // the item walk below then is the literal search :230-314.
+                const uint32_t nw = ctr[0];
+                if (nw >= caps.item_cap) {
+                    P.requeue = true;
+                    break;
+                }
+                __syncwarp();
+                if (lane == 0) ctr[0] = nw + 1u;
+                it_node[nw] = 0;
+                it_edge[nw] = (uint16_t)edge;
+                it_next[nw] = (uint16_t)FNIL;
+                __syncwarp();
+                it = nw;
+                it_node0 = 0;
+                it_next0 = FNIL;
             }
         }
         // add_point(p1), add_point(p2)  :489-490

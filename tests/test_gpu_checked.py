@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHECKED = os.path.join(ROOT, "myrenderer_b200", "lib", "libmyrenderer_b200_checked.so")
 CASES = ("xl_class or app_polygons or known_answer or star_polygons or zigauto or generic_vertex or convex_and_large or size_class or skewed "
-         "or edge_cases or acute or too_large or host_pointers_and_subrange or sound_families or zipper or small_batch")
+         "or edge_cases or acute or too_large or host_pointers_and_subrange or sound_families or zipper or small_batch or repeat_edges")
 
 
 def test_polygon_parity_under_the_checked_build():

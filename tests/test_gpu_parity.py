@@ -337,6 +337,24 @@ def test_generic_vertex_layout_and_odd_unirand_pairs(ctx, oracle):
     assert np.array_equal(b.bbox.cpu().numpy().view(np.uint32), ref["bbox"].view(np.uint32))
 
 
+def test_explicit_orders_that_repeat_edges_every_size_class(ctx, oracle):
+    """An explicit (offset, prime) whose prime shares a factor with n visits some edges several times and others never
+    (unirand.zig:16 is a plain multiply-add-modulo); the reference then runs add_segment on an edge that is already in
+    the DAG.  In the conflict-list classes (n > 64) the edge's list was consumed by the first insertion, so the second
+    search has to restart from the root -- found by scripts/fuzz_parity.py, pinned here for every size class, the team
+    classes and the 3072-point class, with prime 0 (the same edge n times) and offset >= n among the pairs."""
+    sizes = np.array([66, 65, 64, 100, 128, 130, 168, 200, 216, 260, 288, 300, 368, 400, 504, 600, 608, 700, 768, 900, 1024, 1500, 3072, 48, 12])
+    fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    rng = np.random.default_rng(77)
+    for fam in (oracle.FAMILY_ELLIPSE, oracle.FAMILY_ZIPPER, oracle.FAMILY_STAR):
+        xy = oracle.synth_polygons(0xED6E + fam, fp, family=fam)
+        for primes in ((2, 3, 4, 6), (0, 1, 5, 10), (7, 12, 25, 64)):
+            op = np.zeros((len(sizes), 2), dtype=np.uint32)
+            op[:, 0] = rng.integers(0, 5000, len(sizes))
+            op[:, 1] = rng.choice(np.array(primes, dtype=np.uint32), len(sizes))
+            _check_batch(ctx, oracle, xy, fp, offset_prime=op)
+
+
 def test_convex_and_large_polygons(ctx, oracle):
     """Sizes up to 1024 (every shared-memory class) and 1025..4096 (global-memory tier)."""
     rng = np.random.default_rng(5)
