@@ -222,7 +222,9 @@ int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, 
  * (SceneNode.zig:11-22, Terrain.zig:103-110 per tile instead of per terrain): 8 floats
  *     p0 = (min x, min y, min z, 1)   p1 = (max x, max y, max z, 1)
  * over the tile's vertices, positions as defined for mr_terrain_build (x from the row, z from the
- * column, y = height_scale * h).  min/max are exact (comparisons only), so the boxes are bit-exact.
+ * column, y = height_scale * h).  min/max are exact (comparisons only), so the boxes are bit-exact;
+ * a y bound that is zero is written as +0.0f (with height_scale == 0, or a float map holding both
+ * zeros, the sign of a zero bound would otherwise depend on the order of the reduction).
  *
  * mr_terrain_cull applies the reference's visibility test (SceneNode.zig:96-110) to every tile box:
  *     q0 = M * p0 unless some component of p0 is -inf;  q1 = M * p1 unless some component of p1 is +inf

@@ -271,6 +271,23 @@ struct TileArgs {
     float* bbox_out;
 };
 
+// One tile's box from its height extremes, as SceneNode keeps them (p0, p1, w = 1).  Selection by explicit compares
+// (the first operand wins ties) and a zero y bound written as +0: with height_scale == 0 or a map holding both zeros
+// the sign of a zero bound would otherwise depend on the order of the reduction.
+__device__ __forceinline__ void write_tile_box(const TileArgs& a, uint32_t tr, uint32_t tc, uint32_t r0, uint32_t r1, uint32_t c0,
+                                               uint32_t c1, float lo, float hi) {
+    const float org = __fmul_rn(a.origin_scale, (float)a.n);
+    const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
+    const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
+    const float ya = __fmul_rn(a.height_scale, lo), yb = __fmul_rn(a.height_scale, hi);
+    float y0 = yb < ya ? yb : ya, y1 = yb > ya ? yb : ya;
+    y0 = y0 == 0.0f ? 0.0f : y0;
+    y1 = y1 == 0.0f ? 0.0f : y1;
+    float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * ((size_t)tr * a.tiles_c + tc));
+    o[0] = make_float4(xb < xa ? xb : xa, y0, zb < za ? zb : za, 1.0f);
+    o[1] = make_float4(xb > xa ? xb : xa, y1, zb > za ? zb : za, 1.0f);
+}
+
 template <bool U16>
 __global__ void __launch_bounds__(256) terrain_tile_bounds_k(const TileArgs a) {
     const uint32_t t = blockIdx.x;
@@ -302,13 +319,7 @@ __global__ void __launch_bounds__(256) terrain_tile_bounds_k(const TileArgs a) {
             lo = slo[k] < lo ? slo[k] : lo;
             hi = shi[k] > hi ? shi[k] : hi;
         }
-        const float org = __fmul_rn(a.origin_scale, (float)a.n);
-        const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
-        const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
-        const float ya = __fmul_rn(a.height_scale, lo), yb = __fmul_rn(a.height_scale, hi);
-        float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * (size_t)t);
-        o[0] = make_float4(fminf(xa, xb), fminf(ya, yb), fminf(za, zb), 1.0f);
-        o[1] = make_float4(fmaxf(xa, xb), fmaxf(ya, yb), fmaxf(za, zb), 1.0f);
+        write_tile_box(a, tr, tc, r0, r1, c0, c1, lo, hi);
     }
 }
 
@@ -369,8 +380,9 @@ __global__ void __launch_bounds__(256) terrain_tile_bounds_strip_k(const TileArg
         }
     }
     __syncthreads();
-    const uint32_t tc = tc0 + threadIdx.x;
-    if (threadIdx.x < tiles_per_cta && tc < a.tiles_c) {
+    for (uint32_t t = threadIdx.x; t < tiles_per_cta; t += blockDim.x) {  // up to 512 tiles per strip (one-column tiles)
+        const uint32_t tc = tc0 + t;
+        if (tc >= a.tiles_c) break;
         const uint32_t c0 = tc * a.tile_cols, c1 = min(c0 + a.tile_cols, a.n - 1u);
         float lo = __uint_as_float(0x7F800000u), hi = __uint_as_float(0xFF800000u);
         for (uint32_t c = c0; c <= c1; ++c) {
@@ -378,13 +390,7 @@ __global__ void __launch_bounds__(256) terrain_tile_bounds_strip_k(const TileArg
             lo = l < lo ? l : lo;
             hi = h > hi ? h : hi;
         }
-        const float org = __fmul_rn(a.origin_scale, (float)a.n);
-        const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
-        const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
-        const float ya = __fmul_rn(a.height_scale, lo), yb = __fmul_rn(a.height_scale, hi);
-        float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * ((size_t)tr * a.tiles_c + tc));
-        o[0] = make_float4(fminf(xa, xb), fminf(ya, yb), fminf(za, zb), 1.0f);
-        o[1] = make_float4(fmaxf(xa, xb), fmaxf(ya, yb), fmaxf(za, zb), 1.0f);
+        write_tile_box(a, tr, tc, r0, r1, c0, c1, lo, hi);
     }
 }
 
@@ -455,14 +461,7 @@ __global__ void __launch_bounds__(256) terrain_tile_bounds_wide_k(const TileArgs
         lo = __reduce_min_sync(0xFFFFFFFFu, lo);
         hi = __reduce_max_sync(0xFFFFFFFFu, hi);
         if (lane == 0u) {
-            const float hmin = height_from_u16(hi), hmax = height_from_u16(lo);
-            const float org = __fmul_rn(a.origin_scale, (float)a.n);
-            const float xa = __fsub_rn(__fmul_rn(a.grid_step, (float)r0), org), xb = __fsub_rn(__fmul_rn(a.grid_step, (float)r1), org);
-            const float za = __fsub_rn(__fmul_rn(a.grid_step, (float)c0), org), zb = __fsub_rn(__fmul_rn(a.grid_step, (float)c1), org);
-            const float ya = __fmul_rn(a.height_scale, hmin), yb = __fmul_rn(a.height_scale, hmax);
-            float4* o = reinterpret_cast<float4*>(a.bbox_out + 8 * ((size_t)tr * a.tiles_c + tc));
-            o[0] = make_float4(fminf(xa, xb), fminf(ya, yb), fminf(za, zb), 1.0f);
-            o[1] = make_float4(fmaxf(xa, xb), fmaxf(ya, yb), fmaxf(za, zb), 1.0f);
+            write_tile_box(a, tr, tc, r0, r1, c0, c1, height_from_u16(hi), height_from_u16(lo));
         }
     }
 }

@@ -179,7 +179,7 @@ int mr_o_terrain_tile_bounds(const void* height, uint32_t fmt, uint32_t n, uint3
             uint32_t r1 = r0 + tile_rows < n - 1u ? r0 + tile_rows : n - 1u;
             uint32_t c1 = c0 + tile_cols < n - 1u ? c0 + tile_cols : n - 1u;
             float lo = INFINITY, hi = -INFINITY, org = p->origin_scale * (float)n;
-            float xa, xb, za, zb, ya, yb;
+            float xa, xb, za, zb, ya, yb, y0, y1;
             float* o = bbox_out + 8u * ((size_t)tr * tiles_c + tc);
             for (r = r0; r <= r1; ++r)
                 for (c = c0; c <= c1; ++c) {
@@ -193,8 +193,14 @@ int mr_o_terrain_tile_bounds(const void* height, uint32_t fmt, uint32_t n, uint3
             zb = p->grid_step * (float)c1 - org;
             ya = p->height_scale * lo;
             yb = p->height_scale * hi;
-            o[0] = fminf(xa, xb); o[1] = fminf(ya, yb); o[2] = fminf(za, zb); o[3] = 1.0f;
-            o[4] = fmaxf(xa, xb); o[5] = fmaxf(ya, yb); o[6] = fmaxf(za, zb); o[7] = 1.0f;
+            /* explicit compares (first operand wins ties); a zero y bound is written as +0: with height_scale == 0,
+             * or a map that holds both zeros, its sign would otherwise depend on the order of the scan */
+            y0 = yb < ya ? yb : ya;
+            y1 = yb > ya ? yb : ya;
+            if (y0 == 0.0f) y0 = 0.0f;
+            if (y1 == 0.0f) y1 = 0.0f;
+            o[0] = xb < xa ? xb : xa; o[1] = y0; o[2] = zb < za ? zb : za; o[3] = 1.0f;
+            o[4] = xb > xa ? xb : xa; o[5] = y1; o[6] = zb > za ? zb : za; o[7] = 1.0f;
         }
     return MR_OK;
 }

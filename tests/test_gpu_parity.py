@@ -762,6 +762,20 @@ def test_terrain_tiles_and_cull_match_oracle(ctx, oracle):
         hf = oracle.heightmap_normalize(h)
         ctx.check(lib.mr_terrain_tile_bounds(ctx.handle, hf.ctypes.data, 1, n, tr, tc, None, box_h.ctypes.data), "tile bounds")
         assert np.array_equal(box_h.view(np.uint32), want_box.view(np.uint32))
+        if n == 1000:  # one-column tiles (512 tiles per strip), zero and negative height scales
+            for tr2, tc2, prm in ((16, 1, (0.2, 0.1, 5.0)), (7, 1, (0.2, 0.1, 0.0)), (64, 64, (0.2, 0.1, 0.0)), (33, 2, (0.3, -0.5, -4.0))):
+                wb = oracle.terrain_tile_bounds(h, n, tr2, tc2, prm)
+                bd = torch.empty(wb.size, dtype=torch.float32, device="cuda")
+                pp = (C.c_float * 3)(*prm)
+                ctx.check(lib.mr_terrain_tile_bounds(ctx.handle, hd.data_ptr(), 0, n, tr2, tc2, pp, bd.data_ptr()), "tile bounds")
+                ctx.sync()
+                assert np.array_equal(bd.cpu().numpy().view(np.uint32), wb.reshape(-1).view(np.uint32)), (tr2, tc2, prm)
+                hneg = (oracle.heightmap_normalize(h) - np.float32(0.5)) * np.float32(0.0)  # a float map of +0 and -0
+                hneg[::3] = np.float32(-0.0)
+                wb = oracle.terrain_tile_bounds(hneg, n, tr2, tc2, prm)
+                ctx.check(lib.mr_terrain_tile_bounds(ctx.handle, torch.from_numpy(hneg).cuda().data_ptr(), 1, n, tr2, tc2, pp, bd.data_ptr()), "tile bounds")
+                ctx.sync()
+                assert np.array_equal(bd.cpu().numpy().view(np.uint32), wb.reshape(-1).view(np.uint32)), ("zeros", tr2, tc2, prm)
         mats = [camera_matrix(), camera_matrix((5.0, 60.0, 5.0), (40.0, 0.0, 40.0)), mat_image(np.array([[0, 0, 0, 1]] * 4, dtype=np.float32)),
                 mat_image(np.array([[0, 0, 0, -1], [0, 0, 0, 2], [0, 0, 0, 0], [0, 0, 0, 1]], dtype=np.float32))]
         for m in mats:
