@@ -111,48 +111,93 @@ TRANSFORMS = ["identity", "reverse", "rotate_start", "swap_axes", "negate_y", "n
 MIXES = ["small", "small", "tiny", "loguniform", "loguniform", "boundaries", "xl", "few"]
 
 
-def compare(ctx, mr, oracle, xy, fp, *, offset_prime, seed, poly_index0, order, host):
-    """Returns None when every output byte agrees, else a description of the first difference."""
+def draw_layout(rng, which):
+    """(stride, attrs) for GPUVertex-like vertices: x (2 floats) and optionally a colour (3 or 4 floats)."""
+    if which == "decl":
+        return (32, ((0, 2), (16, 3)))
+    if which == "zigauto":
+        return (32, ((16, 2), (0, 3)))
+    for _ in range(100):
+        stride = 4 * int(rng.integers(2, 17))
+        slots = stride // 4
+        a = int(rng.integers(0, slots - 1))
+        if rng.integers(0, 4) == 0:
+            return (stride, ((4 * a, 2),))
+        cc = int(rng.choice([3, 4]))
+        b = int(rng.integers(0, max(slots - cc + 1, 1)))
+        if b + cc <= slots and (a + 2 <= b or b + cc <= a):
+            return (stride, ((4 * a, 2), (4 * b, cc)))
+    return (32, ((0, 2), (16, 3)))
+
+
+def compare(ctx, mr, oracle, xy, fp, *, offset_prime, seed, poly_index0, layout, host, split, skip):
+    """Runs the batch through mr_triangulate_batch -- whole, or cut into sub-range calls that write into the same buffers --
+    and compares every output byte with the oracle.  Returns (None, ref) when they agree, else a description.
+      host : every buffer is plain host memory (staged / small-batch paths) instead of device memory
+      split: None | "abs" (sub-calls index the full xy / vtx buffers: point_base = tri_base = 0)
+                  | "rel" (sub-calls get pointers to their own slices: point_base = first_point[cut], tri_base = first_tri[cut])
+      skip : subset of {"bbox", "status", "ntri"} passed as NULL"""
     import torch
 
-    lay = mr.VertexLayout.create(mr.GPUVertex, order)
-    ref = oracle.polygon_batch(xy, fp, offset_prime=offset_prime, seed=seed, poly_index0=poly_index0,
-                               layout=(lay.stride, lay.attributes), nthreads=0)
+    lay = mr.VertexLayout(layout[0], layout[1])
+    ref = oracle.polygon_batch(xy, fp, offset_prime=offset_prime, seed=seed, poly_index0=poly_index0, layout=layout, nthreads=0)
     npoly = len(fp) - 1
-    if host:  # plain host memory everywhere: the staged / small-batch paths
-        ft = ref["first_tri"].astype(np.uint64)
-        vtx = np.zeros(max(int(ft[-1]) * 3 * lay.stride, 32), dtype=np.uint8)
-        bbox = np.zeros((npoly, 4), dtype=np.float32)
-        st = np.zeros(npoly, dtype=np.uint32)
-        nt = np.zeros(npoly, dtype=np.uint32)
-        p = mr.Polygon(ctx, lay)
-        op = None if offset_prime is None else np.ascontiguousarray(offset_prime, dtype=np.uint32).reshape(-1)
-        p.triangulate(p.job(np.ascontiguousarray(xy, dtype=np.float32), fp, npoly, vtx_out=vtx, first_tri=ft, bbox_out=bbox,
-                            status_out=st, ntri_out=nt, offset_prime=op, seed=seed, poly_index0=poly_index0))
-        gv, gb, gs, gn = vtx[: int(ft[-1]) * 3 * lay.stride], bbox, st, nt
+    stride = layout[0]
+    ft = ref["first_tri"].astype(np.uint64)
+    nv = int(ft[-1]) * 3 * stride
+    op = None if offset_prime is None else np.ascontiguousarray(offset_prime, dtype=np.uint32).reshape(-1)
+    xyh = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1)
+    SENT = 0xA5
+    h = dict(xy=xyh, fp=fp, ft=ft, op=op, vtx=np.full(nv + 32, SENT, dtype=np.uint8), bbox=np.full(4 * npoly, np.float32(-7.0), dtype=np.float32),
+             st=np.full(npoly, 0xA5A5A5A5, dtype=np.uint32), nt=np.full(npoly, 0xA5A5A5A5, dtype=np.uint32))
+    if host:
+        d = h
     else:
-        b = mr.Polygon(ctx, lay).create_polygons(xy, fp, offset_prime=offset_prime, seed=seed, poly_index0=poly_index0)
-        ctx.sync()
-        gv = b.vertex_buffer.cpu().numpy()
-        gb = b.bbox.cpu().numpy()
-        gs = b.status.cpu().numpy().view(np.uint32)
-        gn = b.ntri.cpu().numpy().view(np.uint32)
-        torch.cuda.synchronize()
-    bad = np.where(gs != ref["status"])[0]
-    if bad.size:
-        i = int(bad[0])
-        return "status of polygon %d (n=%d): gpu %d oracle %d (%d differ)" % (i, int(fp[i + 1] - fp[i]), int(gs[i]), int(ref["status"][i]), bad.size)
-    if not np.array_equal(gn, ref["ntri"]):
+        def up(x):
+            if x is None:
+                return None
+            v = x.view(np.int64) if x.dtype == np.uint64 else x.view(np.int32) if x.dtype == np.uint32 else x
+            return torch.from_numpy(v).cuda()
+        d = {k: up(v) for k, v in h.items()}
+    cuts = [0, npoly]
+    if split and npoly >= 2:
+        cuts = sorted(set([0, npoly] + [int(c) for c in np.random.default_rng(seed & 0xFFFF).integers(1, npoly, size=3)]))
+    p = mr.Polygon(ctx, lay)
+    for a, z in zip(cuts[:-1], cuts[1:]):
+        pa, ta = int(fp[a]), int(ft[a])
+        rel = split == "rel"
+        p.triangulate(p.job(d["xy"][2 * pa:] if rel else d["xy"], d["fp"][a:], z - a,
+                            vtx_out=d["vtx"][ta * 3 * stride:] if rel else d["vtx"], first_tri=d["ft"][a:],
+                            bbox_out=None if "bbox" in skip else d["bbox"][4 * a:], status_out=None if "status" in skip else d["st"][a:],
+                            ntri_out=None if "ntri" in skip else d["nt"][a:], offset_prime=None if op is None else d["op"][2 * a:],
+                            seed=seed, poly_index0=poly_index0 + a, point_base=pa if rel else 0, tri_base=ta if rel else 0))
+    ctx.sync()
+    if host:
+        gv, gb, gs, gn = h["vtx"], h["bbox"], h["st"], h["nt"]
+    else:
+        gv, gb = d["vtx"].cpu().numpy(), d["bbox"].cpu().numpy()
+        gs, gn = d["st"].cpu().numpy().view(np.uint32), d["nt"].cpu().numpy().view(np.uint32)
+    if not (gv[nv:] == SENT).all():
+        return "bytes behind the vertex range were written"
+    gv = gv[:nv]
+    if "status" in skip:
+        if not (gs == 0xA5A5A5A5).all():
+            return "status_out was NULL but the buffer was written"
+    else:
+        bad = np.where(gs != ref["status"])[0]
+        if bad.size:
+            i = int(bad[0])
+            return "status of polygon %d (n=%d): gpu %d oracle %d (%d differ)" % (i, int(fp[i + 1] - fp[i]), int(gs[i]), int(ref["status"][i]), bad.size)
+    if "ntri" not in skip and not np.array_equal(gn, ref["ntri"]):
         return "ntri differs"
-    if not np.array_equal(gv, ref["vtx"]):
-        per = lay.stride * 3
-        ftr = ref["first_tri"]
+    if not np.array_equal(gv, ref["vtx"][:nv]):
+        per = stride * 3
         for i in range(npoly):
-            a, z = int(ftr[i]) * per, int(ftr[i + 1]) * per
+            a, z = int(ft[i]) * per, int(ft[i + 1]) * per
             if not np.array_equal(gv[a:z], ref["vtx"][a:z]):
-                return "vertices of polygon %d (n=%d, status %d) differ" % (i, int(fp[i + 1] - fp[i]), int(gs[i]))
+                return "vertices of polygon %d (n=%d, oracle status %d) differ" % (i, int(fp[i + 1] - fp[i]), int(ref["status"][i]))
         return "vertex bytes differ outside every polygon range"
-    if not np.array_equal(gb.view(np.uint32).reshape(-1), ref["bbox"].view(np.uint32).reshape(-1)):
+    if "bbox" not in skip and not np.array_equal(gb.view(np.uint32).reshape(-1), ref["bbox"].view(np.uint32).reshape(-1)):
         return "bbox differs"
     return None, ref
 
@@ -192,12 +237,17 @@ def main():
             op = np.stack([rng.integers(0, 2 ** 31, size=len(n)).astype(np.uint32) % np.maximum(n, 1),
                            rng.choice(np.array([1, 2, 3, 5, 7, 11, 13, 1723, 10001567], dtype=np.uint32), size=len(n))], axis=1)
         host = (mix == "few") or (r % 5 == 2)
-        order = "zigauto" if r % 7 == 3 else "decl"
+        layout = draw_layout(rng, ["decl", "decl", "zigauto", "generic", "generic"][int(rng.integers(0, 5))])
+        split = [None, None, "abs", "rel"][int(rng.integers(0, 4))]
+        skip = [s_ for s_ in ("bbox", "status", "ntri") if rng.integers(0, 6) == 0]
         desc = {"round": r, "mix": mix, "transform": how, "family": int(fam), "npoly": int(len(sizes)), "points": int(fp[-1]),
-                "explicit_order": op is not None, "host_buffers": bool(host), "layout": order}
+                "explicit_order": op is not None, "host_buffers": bool(host), "layout": layout, "split": split, "null_outputs": skip}
         log.write("start " + json.dumps(desc) + "\n")
         log.flush()
-        res = compare(ctx, mr, orc, xy, fp, offset_prime=op, seed=seed, poly_index0=idx0, order=order, host=host)
+        try:
+            res = compare(ctx, mr, orc, xy, fp, offset_prime=op, seed=seed, poly_index0=idx0, layout=layout, host=host, split=split, skip=skip)
+        except Exception as e:  # an error code for a job this script believes valid is a finding too
+            res = "raised " + repr(e)
         if isinstance(res, tuple):
             ok = int((res[1]["status"] == 0).sum())
             desc["status_ok"] = ok
