@@ -133,7 +133,8 @@ def draw_layout(rng, which):
 def compare(ctx, mr, oracle, xy, fp, *, offset_prime, seed, poly_index0, layout, host, split, skip):
     """Runs the batch through mr_triangulate_batch -- whole, or cut into sub-range calls that write into the same buffers --
     and compares every output byte with the oracle.  Returns (None, ref) when they agree, else a description.
-      host : every buffer is plain host memory (staged / small-batch paths) instead of device memory
+      host : False (device memory) | True / "host" (pageable host memory: staged / small-batch paths) | "pinned" |
+             a dict placing each buffer on its own ("dev" / "host" / "pinned")
       split: None | "abs" (sub-calls index the full xy / vtx buffers: point_base = tri_base = 0)
                   | "rel" (sub-calls get pointers to their own slices: point_base = first_point[cut], tri_base = first_tri[cut])
       skip : subset of {"bbox", "status", "ntri"} passed as NULL"""
@@ -150,15 +151,24 @@ def compare(ctx, mr, oracle, xy, fp, *, offset_prime, seed, poly_index0, layout,
     SENT = 0xA5
     h = dict(xy=xyh, fp=fp, ft=ft, op=op, vtx=np.full(nv + 32, SENT, dtype=np.uint8), bbox=np.full(4 * npoly, np.float32(-7.0), dtype=np.float32),
              st=np.full(npoly, 0xA5A5A5A5, dtype=np.uint32), nt=np.full(npoly, 0xA5A5A5A5, dtype=np.uint32))
-    if host:
-        d = h
-    else:
-        def up(x):
-            if x is None:
-                return None
-            v = x.view(np.int64) if x.dtype == np.uint64 else x.view(np.int32) if x.dtype == np.uint32 else x
-            return torch.from_numpy(v).cuda()
-        d = {k: up(v) for k, v in h.items()}
+    # where each buffer lives: "host" (pageable), "pinned" (page-locked: outputs are written zero-copy) or "dev"
+    def signed(x):
+        return x.view(np.int64) if x.dtype == np.uint64 else x.view(np.int32) if x.dtype == np.uint32 else x
+    d, back = {}, {}
+    for k, v in h.items():
+        where = host if isinstance(host, str) else ("host" if host else "dev")
+        if isinstance(host, dict):
+            where = host[k]
+        if v is None:
+            d[k] = None
+        elif where == "host":
+            d[k] = v
+        elif where == "pinned":
+            t = torch.empty(v.shape, dtype=torch.from_numpy(signed(v)).dtype, pin_memory=True)
+            t.copy_(torch.from_numpy(signed(v)))
+            d[k] = t
+        else:
+            d[k] = torch.from_numpy(signed(v)).cuda()
     cuts = [0, npoly]
     if split and npoly >= 2:
         cuts = sorted(set([0, npoly] + [int(c) for c in np.random.default_rng(seed & 0xFFFF).integers(1, npoly, size=3)]))
@@ -172,11 +182,11 @@ def compare(ctx, mr, oracle, xy, fp, *, offset_prime, seed, poly_index0, layout,
                             ntri_out=None if "ntri" in skip else d["nt"][a:], offset_prime=None if op is None else d["op"][2 * a:],
                             seed=seed, poly_index0=poly_index0 + a, point_base=pa if rel else 0, tri_base=ta if rel else 0))
     ctx.sync()
-    if host:
-        gv, gb, gs, gn = h["vtx"], h["bbox"], h["st"], h["nt"]
-    else:
-        gv, gb = d["vtx"].cpu().numpy(), d["bbox"].cpu().numpy()
-        gs, gn = d["st"].cpu().numpy().view(np.uint32), d["nt"].cpu().numpy().view(np.uint32)
+    def fetch(k):
+        x = d[k]
+        return x if isinstance(x, np.ndarray) else x.cpu().numpy()
+    gv, gb = fetch("vtx"), fetch("bbox")
+    gs, gn = fetch("st").view(np.uint32), fetch("nt").view(np.uint32)
     if not (gv[nv:] == SENT).all():
         return "bytes behind the vertex range were written"
     gv = gv[:nv]
@@ -237,11 +247,15 @@ def main():
             op = np.stack([rng.integers(0, 2 ** 31, size=len(n)).astype(np.uint32) % np.maximum(n, 1),
                            rng.choice(np.array([1, 2, 3, 5, 7, 11, 13, 1723, 10001567], dtype=np.uint32), size=len(n))], axis=1)
         host = (mix == "few") or (r % 5 == 2)
+        if r % 5 in (3, 4) or (mix == "few" and r % 2):  # every buffer placed on its own
+            host = {k: str(rng.choice(["dev", "host", "pinned"])) for k in ("xy", "fp", "ft", "op", "vtx", "bbox", "st", "nt")}
+        elif r % 10 == 7:
+            host = "pinned"
         layout = draw_layout(rng, ["decl", "decl", "zigauto", "generic", "generic"][int(rng.integers(0, 5))])
         split = [None, None, "abs", "rel"][int(rng.integers(0, 4))]
         skip = [s_ for s_ in ("bbox", "status", "ntri") if rng.integers(0, 6) == 0]
         desc = {"round": r, "mix": mix, "transform": how, "family": int(fam), "npoly": int(len(sizes)), "points": int(fp[-1]),
-                "explicit_order": op is not None, "host_buffers": bool(host), "layout": layout, "split": split, "null_outputs": skip}
+                "explicit_order": op is not None, "host_buffers": host, "layout": layout, "split": split, "null_outputs": skip}
         log.write("start " + json.dumps(desc) + "\n")
         log.flush()
         try:

@@ -84,19 +84,26 @@ def draw_layout(rng):
 
 
 def run_build(ctx, t, torch, hs, n, host, rb, re, qb, qe, hlo, hhi, v0, q0, vbytes, icount):
-    if host:
-        gv = np.full(max(vbytes, 1), 0xA5, dtype=np.uint8)
-        gi = np.full(max(icount, 2), 0xA5A5A5A5, dtype=np.uint32)
-        t.build(t.job(hs, n, rows=(rb, re), qrows=(qb, qe), height_row0=hlo, height_rows=hhi - hlo, vtx_out=gv if vbytes else None,
-                      vtx_row0=v0, idx_out=gi if icount else None, idx_qrow0=q0))
-        return gv, gi
-    hd = torch.from_numpy(hs.view(np.int16) if hs.dtype == np.uint16 else hs).cuda()
-    gvd = torch.full((max(vbytes, 1),), 0xA5, dtype=torch.uint8, device="cuda")
-    gid = torch.from_numpy(np.full(max(icount, 2), 0xA5A5A5A5, dtype=np.uint32).view(np.int32)).cuda()
-    t.build(t.job(hd, n, rows=(rb, re), qrows=(qb, qe), height_row0=hlo, height_rows=hhi - hlo, vtx_out=gvd if vbytes else None,
-                  vtx_row0=v0, idx_out=gid if icount else None, idx_qrow0=q0))
+    """host: {"height"|"vtx"|"idx": "dev"|"host"|"pinned"} -- every buffer placed on its own."""
+    def place(x, where):
+        if where == "host":
+            return x
+        v = x.view(np.int16) if x.dtype == np.uint16 else x.view(np.int32) if x.dtype == np.uint32 else x
+        if where == "pinned":
+            tt = torch.empty(v.shape, dtype=torch.from_numpy(v).dtype, pin_memory=True)
+            tt.copy_(torch.from_numpy(v))
+            return tt
+        return torch.from_numpy(v).cuda()
+    hd = place(hs, host["height"])
+    gv = place(np.full(max(vbytes, 1), 0xA5, dtype=np.uint8), host["vtx"])
+    gi = place(np.full(max(icount, 2), 0xA5A5A5A5, dtype=np.uint32), host["idx"])
+    j = t.job(hd, n, rows=(rb, re), qrows=(qb, qe), height_row0=hlo, height_rows=hhi - hlo, vtx_out=gv if vbytes else None,
+              vtx_row0=v0, idx_out=gi if icount else None, idx_qrow0=q0)
+    j.height_fmt = 0 if hs.dtype == np.uint16 else 1
+    t.build(j)
     ctx.sync()
-    return gvd.cpu().numpy(), gid.cpu().numpy().view(np.uint32)
+    back = lambda x: x if isinstance(x, np.ndarray) else x.cpu().numpy()
+    return back(gv), back(gi).view(np.uint32)
 
 
 def main():
@@ -134,7 +141,9 @@ def main():
         params = draw_params(rng)
         lay_t = draw_layout(rng)
         lay = mr.VertexLayout(lay_t[0], lay_t[1])
-        host = bool(rng.integers(0, 3) == 0)
+        k = int(rng.integers(0, 4))
+        host = ({x: "dev" for x in ("height", "vtx", "idx")} if k == 0 else {x: "host" for x in ("height", "vtx", "idx")} if k == 1
+                else {x: str(rng.choice(["dev", "host", "pinned"])) for x in ("height", "vtx", "idx")})
         # a band of rows / quad rows written into a buffer that starts at an earlier row
         if n > 2 and rng.integers(0, 2):
             rb = int(rng.integers(0, n))
