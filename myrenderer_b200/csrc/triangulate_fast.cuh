@@ -46,7 +46,8 @@ struct mr_span {
     int line;
     __device__ __forceinline__ T& operator[](size_t i) const {
         if (i >= n) {
-            printf("MR_CHECKED: index %llu out of range %u (span declared at triangulate_fast.cuh:%d)\n", (unsigned long long)i, n, line);
+            printf("MR_CHECKED: index %llu out of range %u (span declared at triangulate_fast.cuh:%d; block %u thread %u)\n",
+                   (unsigned long long)i, n, line, blockIdx.x, threadIdx.x);
             __trap();
         }
         return p[i];
@@ -67,6 +68,12 @@ struct mr_span {
 #define MR_SPAN_IS_NULL(s) ((s) == nullptr)
 #define MR_SPAN_RAW(s) (s)
 #endif
+
+__device__ __forceinline__ uint32_t mr_lds_u16(uint32_t shared_addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(shared_addr));
+    return v;
+}
 
 constexpr uint32_t FNIL14 = 0x1FFFu;  // null in the 13-bit pa field (ranks are < 1024 on this path)
 constexpr uint32_t CRUMB_RIGHT = 0x2000u;  // segment node: crumb == child2 (the inside is on the right)
@@ -121,7 +128,7 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
     L.orig = o;    o += k.item_cap ? 0 : align16((size_t)k.nmax * 2);  // conflict-list classes: see below
     L.rk = o;      o += align16((size_t)k.nmax * 2);
     L.loc = o;     o += align16((size_t)k.nmax * 2);
-    L.cstack = o;  o += k.item_cap ? 0 : align16((size_t)k.nmax * 2);  // only the search from the root uses it
+    L.cstack = o;  o += k.item_cap ? 0 : align16((size_t)k.nmax * 4);  // 2n entries; only the search from the root uses it
     L.stack = o;   o += align16((size_t)k.stack_cap * 2);
     L.nodes = o;   o += align16((size_t)k.node_cap * 8);
     // mountain-phase arrays reuse what is dead once part 1 is done: the item pool (with the per-edge
@@ -152,7 +159,7 @@ __host__ __device__ inline FLayout fast_layout(const FCaps& k) {
         L.ctr = o;     o += 16;
         if (o < mountain_end) o = mountain_end;
     } else if (!k.par_separate_out) {
-        // n <= 64 class: the same overlays (there mstart takes rk+loc+cstack+stack = 8n bytes >= 2*(add_cap+1))
+        // n <= 64 class: the same overlays (there mstart takes rk+loc+cstack+stack = 10n bytes >= 2*(add_cap+1))
         L.mcount = L.nodes + (size_t)k.add_cap * 4;   // = cum
         L.add_m = L.nodes + (size_t)k.add_cap * 16;   // = S
         L.mstart = L.rk;
@@ -303,29 +310,62 @@ struct FPoly {
     // the walk has produced `give_up` leaves without finishing (the caller then redoes it in parallel).
     __device__ int search_from_root(uint32_t up, uint32_t lo, uint32_t give_up) {
         const float2 Pu = sxy[up], Pl = sxy[lo];
-        uint32_t base = 0, ncr = 0;
+        uint32_t base = 0;
+        // The breadcrumb stack.  A pending breadcrumb is a point node on the path to the current node, and every call of
+        // add_point creates at most one point node: at most 2n of them exist (on a consistent DAG n, of which n - 2 can
+        // lie between the endpoints; the reference's failing cases can hold several nodes of one point).  The stack has
+        // 2n entries, so it cannot overflow and the push is branch-free: the node is always stored into the next free
+        // slot, and the slot is kept only for a breadcrumb.  A running shared-memory address in the product build (one
+        // store and one predicated add per visit), an index into the bounds-checked span in the checked build.
+#ifdef MR_CHECKED
+        uint32_t ncr = 0;
+#define MR_CR_PUSH_IF(c, x) (cstack[ncr] = (uint16_t)(x), ncr += (c) ? 1u : 0u)
+#define MR_CR_EMPTY() (ncr == 0u)
+#define MR_CR_POP() (cstack[--ncr])
+#else
+        // (a 32-bit shared-window address: as a C++ pointer the compiler carries the generic pointer beside it)
+        const uint32_t cr0 = (uint32_t)__cvta_generic_to_shared(cstack);
+        uint32_t cr = cr0;
+#define MR_CR_PUSH_IF(c, x)                                                                      \
+    do {                                                                                         \
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(cr), "h"((unsigned short)(x)));             \
+        if (c) cr += 2u;                                                                         \
+    } while (0)
+#define MR_CR_EMPTY() (cr == cr0)
+#define MR_CR_POP() (cr -= 2u, mr_lds_u16(cr))
+#endif
         nstack = 0;
+        static_assert(T_POINT == 0 && T_SEGMENT == 1 && T_TRAPEZOID == 2 && FNIL == 0xFFFFu, "the word tests below read these bits");
+        // A point node's second word is 0xFFFF0000 | rank (pb = FNIL, type 0, crumb 0, rank < 0x2000): as a signed
+        // number it lies below every other node's (segment nodes and trapezoids with a lower point are positive,
+        // trapezoids without one are 0xFFFF8000 | ...).  The run of point nodes -- a quarter of all instructions of
+        // the n <= 64 kernel -- therefore tests the type and compares the rank on the whole word: no masks.
+        const int up_w = (int)(0xFFFF0000u | up), lo_w = (int)(0xFFFF0000u | lo), point_end = (int)0xFFFF2000u;
         for (;;) {      // loop1 :231
             uint2 v = nd[base];
             for (;;) {  // loop :232, with runs of point nodes in a loop of their own
-                while (type_of(v.y) == T_POINT) {
-                    const uint32_t pa = v.y & FNIL14;
-                    const bool first = pa > up;
-                    if (first && pa < lo) cstack[ncr++] = (uint16_t)base;
+                int y = (int)v.y;
+                while (y < point_end) {
+                    const bool first = y > up_w;  // :234-259 collapsed, see dfs_step
+                    MR_CR_PUSH_IF(first & (y < lo_w), base);  // up above pa above lo: breadcrumb, child2 comes later
                     base = first ? (v.x & 0xFFFFu) : (v.x >> 16);
                     v = nd[base];
+                    y = (int)v.y;
                 }
-                if (type_of(v.y) == T_TRAPEZOID) break;
+                if ((v.y & 0xFFFFu) >= 0x8000u) break;  // a trapezoid
                 bool both;
                 base = dfs_step(v, up, lo, Pu, Pl, &both);  // a segment node: never a breadcrumb
                 v = nd[base];
             }
             if (!push(base)) return 0;  // :302
-            if (ncr == 0) break;        // :306-313
+            if (MR_CR_EMPTY()) break;   // :306-313
             if (nstack >= give_up) return 2;
-            base = nd[cstack[--ncr]].x >> 16;
+            base = nd[MR_CR_POP()].x >> 16;
         }
         return 1;
+#undef MR_CR_PUSH_IF
+#undef MR_CR_EMPTY
+#undef MR_CR_POP
     }
 
     // The same search as a lane-parallel frontier expansion, for the searches that explode (the same
@@ -349,6 +389,7 @@ struct FPoly {
         __syncwarp();
         for (;;) {
             const uint32_t cnt = min(ctr[0], cap);
+            __syncwarp();  // every lane has read the count before any lane's atomicAdd moves it (lanes need not run in lock-step)
             bool advanced = false;
             for (uint32_t it = lane; it < cnt; it += 32) {
                 uint32_t node = it_node[it];
@@ -814,7 +855,7 @@ __device__ __forceinline__ void team_refresh(MR_SPAN(const float2) sxy, MR_SPAN(
             team_sync<W>();  // every append of this round is done
             start = end;
             end = min(I.ctr[0], I.cap);
-            if (W > 1) team_bar<W>();  // everyone has read the counter before the next round moves it
+            team_sync<W>();  // everyone has read the counter before the next round moves it
         }
     }
 }
@@ -1220,7 +1261,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
     P.sxy = sxy;
     P.nd = MR_MAKE_SPAN(uint2, reinterpret_cast<uint2*>(ws + L.nodes), caps.node_cap);
     P.stack = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.stack), caps.stack_cap);
-    P.cstack = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.cstack), caps.item_cap ? 0u : caps.nmax);
+    P.cstack = MR_MAKE_SPAN(uint16_t, reinterpret_cast<uint16_t*>(ws + L.cstack), caps.item_cap ? 0u : 2u * caps.nmax);
     P.gstack = MR_SPAN_NULL(uint16_t);
     P.nnodes = 1;  // :479 root trapezoid
     P.nstack = 0;
@@ -1350,6 +1391,7 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
                         __syncwarp();
                         start = end;
                         end = min(ctr[0], caps.item_cap);
+                        __syncwarp();  // every lane has read the counter before the next round moves it
                     }
                     if (ctr[1]) {  // pool exhausted: the next tier redoes this polygon with the literal search
                         P.requeue = true;
