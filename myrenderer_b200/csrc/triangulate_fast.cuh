@@ -226,6 +226,8 @@ struct FPoly {
     // the descent of add_point (:144-167) from `base`; returns the trapezoid, or FNIL when the walk
     // meets the point's own node (already inserted)
     __device__ __forceinline__ uint32_t locate(uint32_t pid, float2 P, uint32_t base) const {
+        // (the whole-word tests of search_from_root were tried here too: no gain for n <= 64, 2.6 % slower in the
+        // conflict-list classes)
         for (;;) {
             const uint2 v = nd[base];
             const uint32_t t = type_of(v.y);
@@ -1256,6 +1258,25 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         unirand_seed_warp(n, a.seed, a.poly_index0 + pi, lane, &ur_offset, &ur_prime);
     }
 
+    if (ITEMS && a.offset_prime) {
+        // An explicit (offset, prime) pair can come back to an edge it has inserted already (unirand.zig:16 is a plain
+        // multiply-add-modulo; unirand_seed only hands out primes that do not divide n), and the reference then searches
+        // and splits again (:493).  An edge's conflict list is consumed by its first insertion, so such polygons take the
+        // literal search from the root: the next tier.  The order repeats iff gcd(prime, n) > 1 when both values are
+        // below n; with larger values the u32 product wraps and the order is not an arithmetic progression mod n at all.
+        bool repeats = ur_offset >= n || ur_prime >= n;
+        if (!repeats) {
+            uint32_t g = n, h = ur_prime;
+            while (h) {
+                const uint32_t t = g % h;
+                g = h;
+                h = t;
+            }
+            repeats = g != 1u;
+        }
+        if (repeats) return F_REQUEUE_SPEC;
+    }
+
     // ---- part 1: trapezoidation ---------------------------------------------------------------------
     FPoly P;
     P.sxy = sxy;
@@ -1444,28 +1465,9 @@ __device__ int process_polygon_fast(const BatchArgs& a, uint32_t pi, unsigned ch
         uint32_t it = FNIL, it_node0 = 0, it_next0 = FNIL;
         if (use_items) {
             it = ehead[edge];
-            if (it != FNIL) {
+            if (it != FNIL) {  // always: orders that come back to an edge were sent to the next tier above
                 it_node0 = it_node[it];
                 it_next0 = it_next[it];
-            } else {
-                // An explicit (offset, prime) pair whose prime divides n comes back to an edge it has inserted already
-                // (unirand.zig:16 does not care), and the reference searches and splits again (:493).  The edge's
-                // conflict list was consumed the first time, so the search restarts from a fresh item at the root:
-                // the item walk below then is the literal search :230-314.
-                const uint32_t nw = ctr[0];
-                if (nw >= caps.item_cap) {
-                    P.requeue = true;
-                    break;
-                }
-                __syncwarp();
-                if (lane == 0) ctr[0] = nw + 1u;
-                it_node[nw] = 0;
-                it_edge[nw] = (uint16_t)edge;
-                it_next[nw] = (uint16_t)FNIL;
-                __syncwarp();
-                it = nw;
-                it_node0 = 0;
-                it_next0 = FNIL;
             }
         }
         // add_point(p1), add_point(p2)  :489-490

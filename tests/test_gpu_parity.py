@@ -340,9 +340,10 @@ def test_generic_vertex_layout_and_odd_unirand_pairs(ctx, oracle):
 def test_explicit_orders_that_repeat_edges_every_size_class(ctx, oracle):
     """An explicit (offset, prime) whose prime shares a factor with n visits some edges several times and others never
     (unirand.zig:16 is a plain multiply-add-modulo); the reference then runs add_segment on an edge that is already in
-    the DAG.  In the conflict-list classes (n > 64) the edge's list was consumed by the first insertion, so the second
-    search has to restart from the root -- found by scripts/fuzz_parity.py, pinned here for every size class, the team
-    classes and the 3072-point class, with prime 0 (the same edge n times) and offset >= n among the pairs."""
+    the DAG.  In the conflict-list classes (n > 64) the edge's list was consumed by the first insertion and the second
+    search found nothing (scripts/fuzz_parity.py found it); such orders are now recognised up front (gcd(prime, n) > 1,
+    or values >= n whose u32 product wraps) and take the literal search of the next tier.  Pinned here for every size
+    class, the team classes and the 3072-point class, with prime 0 (the same edge n times) and offset >= n among the pairs."""
     sizes = np.array([66, 65, 64, 100, 128, 130, 168, 200, 216, 260, 288, 300, 368, 400, 504, 600, 608, 700, 768, 900, 1024, 1500, 3072, 48, 12])
     fp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
     rng = np.random.default_rng(77)
