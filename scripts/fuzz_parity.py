@@ -7,7 +7,9 @@ and size mixes around every class boundary.  Test infrastructure: the oracle is 
     python scripts/fuzz_parity.py --rounds 60 --seed 1 --out gpurun_out/fuzz.json     # on a GPU box
     MR_B200_LIB=myrenderer_b200/lib/libmyrenderer_b200_checked.so python scripts/fuzz_parity.py ...   # bounds-checked build
 
-Every case appends one line to <out>.log before and after it runs, so a hang names its case."""
+Every case appends one line to <out>.log before and after it runs, so a hang names its case.
+On a shared GPU box always run it under `timeout -s KILL <seconds>`: --budget-s only stops NEW cases from starting.
+"""
 import argparse
 import json
 import os

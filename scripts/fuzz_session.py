@@ -5,6 +5,8 @@ from one call into the next (scratch growth and trim, the cached launch plan, si
 Test infrastructure: the oracle is the checker.
 
     python scripts/fuzz_session.py --steps 400 --seed 1 --out gpurun_out/fuzz_session.json     # on a GPU box
+
+On a shared GPU box always run it under `timeout -s KILL <seconds>`: --budget-s only stops NEW cases from starting.
 """
 import argparse
 import ctypes as C

@@ -5,6 +5,8 @@ layouts (strides 12..64, position / normal at any 4-byte offset, with and withou
 larger buffers, device and host pointers, tilings and cull matrices.  Test infrastructure: the oracle is the checker.
 
     python scripts/fuzz_terrain.py --rounds 300 --seed 1 --out gpurun_out/fuzz_terrain.json     # on a GPU box
+
+On a shared GPU box always run it under `timeout -s KILL <seconds>`: --budget-s only stops NEW cases from starting.
 """
 import argparse
 import ctypes as C
