@@ -108,3 +108,37 @@ def test_cull_compaction_and_index_ranges(oracle):
     assert none["visible"].all()
     none = oracle.terrain_cull(box, n, tr, tc, mat_image(np.array([[0, 0, 0, -1], [0, 0, 0, 2], [0, 0, 0, 0], [0, 0, 0, 1]], dtype=np.float32)))
     assert not none["visible"].any() and int(none["counts"][0]) == 0 and none["idx"].size == 0
+
+
+def test_height_conversion_is_monotone_so_tile_extremes_can_be_taken_on_texels(oracle):
+    """terrain_tile_bounds_wide_k reduces the raw u16 texels (packed min / max) and converts only the two results:
+    exact because 1 - v/65535 (Terrain.zig:120) is monotone non-increasing over all 65,536 texel values, so the smallest
+    height of a tile is the height of its largest texel and vice versa."""
+    h = oracle.heightmap_normalize(np.arange(65536, dtype=np.uint16))
+    assert (np.diff(h) <= 0).all() and h[0] == 1.0 and h[65535] == 0.0
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        t = rng.integers(0, 65536, size=int(rng.integers(1, 400))).astype(np.uint16)
+        ht = oracle.heightmap_normalize(t)
+        assert ht.min() == h[int(t.max())] and ht.max() == h[int(t.min())]
+
+
+def test_tile_box_zero_bounds_are_positive_zero_and_one_column_tiles(oracle):
+    """A y bound that is zero is written as +0.0f whatever the order of the reduction (height_scale == 0, or a float map
+    holding both zeros); tiles one quad wide give n - 1 tiles per row (the strip kernels take 512 of them per CTA)."""
+    n = 40
+    h = np.zeros((n, n), dtype=np.float32)
+    h[::2] = np.float32(-0.0)
+    h[1, 1] = np.float32(-3.0)
+    for prm in ((0.2, 0.1, 0.0), (0.2, 0.1, 5.0), (0.2, 0.1, -2.0)):
+        box = oracle.terrain_tile_bounds(h, n, 4, 1, prm)
+        assert box.shape[0] == ((n - 1 + 3) // 4) * (n - 1)
+        y = box[:, [1, 5]].copy().view(np.uint32)
+        assert not (y == 0x80000000).any(), prm  # no negative zero
+        assert (box[:, 1] <= box[:, 5]).all()
+    u = oracle.synth_heightmap_u16(9, n)
+    box = oracle.terrain_tile_bounds(u, n, 7, 1)
+    hf = oracle.heightmap_normalize(u)
+    for tc in (0, 17, n - 2):
+        lo = hf[0:8, tc:tc + 2].min() * np.float32(5.0)
+        assert box[tc, 1] == np.float32(lo)
