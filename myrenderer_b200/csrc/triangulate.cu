@@ -494,12 +494,23 @@ __device__ __forceinline__ bool angle_clear_of_pi(float dy, float dx) {
 // Same value as is_acute.  When both angles are certainly in [0, pi - 7e-7], |a - b| <= max(a, b) < (f32)pi without
 // evaluating them -- the case of every triangle of a sorted mountain except a centre that sees a neighbour
 // within 1e-6 rad of the negative x axis, which takes the exact evaluation.
+#ifdef MR_OUTLINE_COLD
+__noinline__ __device__ bool is_acute_exact_outlined(float2 P, float2 A1, float2 A2) {
+    const float a = dev_atan2f(__fsub_rn(P.y, A1.y), __fsub_rn(P.x, A1.x));
+    const float b = dev_atan2f(__fsub_rn(P.y, A2.y), __fsub_rn(P.x, A2.x));
+    return fabsf(__fsub_rn(a, b)) < __uint_as_float(0x40490fdbu);
+}
+#endif
 __device__ __forceinline__ bool is_acute_shortcut(const float2* pts, uint32_t point, uint32_t axis1, uint32_t axis2) {
     const float2 P = pts[point], A1 = pts[axis1], A2 = pts[axis2];
     if (angle_clear_of_pi(__fsub_rn(P.y, A1.y), __fsub_rn(P.x, A1.x)) &&
         angle_clear_of_pi(__fsub_rn(P.y, A2.y), __fsub_rn(P.x, A2.x)))
         return true;
+#ifdef MR_OUTLINE_COLD
+    return is_acute_exact_outlined(P, A1, A2);
+#else
     return is_acute(pts, point, axis1, axis2);
+#endif
 }
 
 // emit order of Triangulation.zig:405-422; returns ids packed, count in *cnt (3, or 1 when an
@@ -574,13 +585,28 @@ struct Sink {
         }
     }
     // zero vertices [k0, k1) cooperatively
+    // -DMR_OUTLINE_COLD (experiment, off by default): zero() and the exact acute test out of
+    // line -- a sixth of the n <= 64 kernel's code, which runs short of instruction cache: measured -2..-4 % on that
+    // kernel.  Out of line the 256-bit asm store of one repeated operand was compiled as a 32-bit store, hence the
+    // plain stores under the flag.  Not shipped: the bounds-checked build did not finish its fuzz run with it.
+#ifdef MR_OUTLINE_COLD
+    __noinline__
+#endif
     __device__ void zero(uint32_t k0, uint32_t k1, uint32_t lane, uint32_t nthreads = 32u) const {
         if (k1 <= k0) return;
         if (fast32) {
+#ifdef MR_OUTLINE_COLD
+            for (uint32_t k = k0 + lane; k < k1; k += nthreads) {
+                uint4* p = reinterpret_cast<uint4*>(base + (size_t)k * 32);
+                p[0] = make_uint4(0u, 0u, 0u, 0u);
+                p[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+#else
             for (uint32_t k = k0 + lane; k < k1; k += nthreads)
                 asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(base + (size_t)k * 32),
                              "f"(0.0f)
                              : "memory");
+#endif
         } else {
             uint32_t* w = reinterpret_cast<uint32_t*>(base + (size_t)k0 * stride);
             const size_t words = (size_t)(k1 - k0) * stride / 4;
