@@ -342,3 +342,48 @@ def test_synthetic_polygons_are_simple_and_positively_oriented(oracle):
     fpl = oracle.synth_polygon_sizes(0x5EED0005, 2000, 8, 1024, dist=1)
     nl = np.diff(fpl.astype(np.int64))
     assert nl.min() >= 8 and nl.max() <= 1024 and 150 < nl.mean() < 270
+
+
+def test_independent_restatement_agrees_on_fuzzed_inputs_and_repeating_orders(oracle):
+    """The same cross-check on the inputs the GPU fuzz draws (scripts/fuzz_parity.py): the three synthetic families under
+    reversal, axis swap, quantised coordinates (ties), collinear runs, duplicated vertices and random rings -- and with
+    explicit edge orders whose prime shares a factor with n, so that add_segment runs on an edge that is already in the
+    DAG (the case the conflict-list kernels once got wrong: what the reference does there is pinned by two restatements)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "scripts"))
+    import fuzz_parity as FP
+    from oracle import pyref
+
+    rng = np.random.default_rng(2026)
+    atan2 = lambda y, x: np.float32(oracle.atan2f(y, x))
+    fams = [oracle.FAMILY_STAR, oracle.FAMILY_ELLIPSE, oracle.FAMILY_ZIPPER]
+    hows = ["identity", "reverse", "swap_axes", "quantise", "collinear", "duplicate", "noise", "noise_grid", "same_y"]
+    checked = repeats = fails = 0
+    for trial in range(160):
+        n = int(rng.integers(3, 19))
+        fp = np.array([0, n], dtype=np.uint64)
+        P = FP.transform(rng, oracle.synth_polygons(1000 + trial, fp, family=fams[trial % 3]), fp, hows[trial % len(hows)])
+        P = np.ascontiguousarray(P, dtype=np.float32).reshape(n, 2)
+        if trial % 2:
+            off, prime = int(rng.integers(0, n)), int(rng.choice([0, 1, 2, 3, 4, 6]))
+            repeats += int(np.gcd(prime, n) != 1)
+        else:
+            off, prime = oracle.unirand_seed(n, 77, trial)
+        order = oracle.unirand_sequence(n, off, prime)
+        r = oracle.polygon_batch(P, fp, offset_prime=[off, prime])
+        st_c = int(r["status"][0])
+        if st_c & ~(4 | 8 | 128):  # arena caps, coincident-point or non-finite statuses: outside pyref's vocabulary
+            continue
+        ids, st = pyref.triangulate_ids(P, order, atan2=atan2)
+        cap = 3 * (n - 2)
+        if st == "null_unwrap":
+            assert st_c & 4, (trial, n, off, prime)
+            fails += 1
+        else:
+            exp = np.full(max(cap, 1), 0xFFFFFFFF, dtype=np.uint32)
+            m = min(cap, len(ids))
+            exp[:m] = ids[:m]
+            assert np.array_equal(exp[:cap], r["ids"][:cap]), (trial, n, off, prime, hows[trial % len(hows)])
+            assert (len(ids) > cap) == bool(st_c & 8) and (len(ids) < cap) == bool(st_c & 128)
+        checked += 1
+    assert checked >= 120 and repeats >= 20 and fails > 0
