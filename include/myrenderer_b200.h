@@ -239,7 +239,9 @@ int mr_heightmap_normalize(mr_context* ctx, const uint16_t* in, uint64_t count, 
  *     idx_out             compacted index buffer: the visible tiles in ascending order, each tile's quads
  *                         row-major, six indices per quad exactly as mr_terrain_build writes them --
  *                         one drawIndexed(counts_out[1]) draws what survives the cull
- *     counts_out[2]       {visible tiles, indices written} as uint64 */
+ *     counts_out[2]       {visible tiles, indices written} as uint64
+ * Alignment (MR_E_BADARG otherwise): bbox_out of mr_terrain_tile_bounds 16 bytes (a box is two float4),
+ * idx_out of mr_terrain_cull 8 bytes. */
 int mr_terrain_tile_count(uint32_t n, uint32_t tile_rows, uint32_t tile_cols, uint32_t* tiles_r_out,
                           uint32_t* tiles_c_out);
 int mr_terrain_tile_bounds(mr_context* ctx, const void* height, uint32_t height_fmt, uint32_t n,
